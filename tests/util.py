@@ -1,0 +1,35 @@
+"""Shared helpers for the parity tests: golden loaders and oracle construction."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def golden(name):
+    with np.load(os.path.join(GOLDEN, name + '.npz')) as z:
+        return {k: torch.from_numpy(z[k]) if z[k].dtype.kind in 'fiub' else z[k] for k in z.files}
+
+
+def reference_score_table():
+    """[1000,1000] IGSO(3) score-norm table holding the REFERENCE's rows (tests/golden/igso3.npz) at
+    every sigma index any golden uses; NaN elsewhere so an unexpected row is caught."""
+    g = golden('igso3')
+    tab = torch.full((1000, 1000), float('nan'))
+    tab[g['rows'].long()] = g['score_norms']
+    cdf = torch.full((1000, 1000), float('nan'))
+    cdf[g['rows'].long()] = g['cdf']
+    pdf = torch.full((1000, 1000), float('nan'))
+    pdf[g['rows'].long()] = g['pdf']
+    return tab, cdf, pdf
+
+
+def oracle_diffuser():
+    from oracle.diffusers import OracleDiffuser
+    tab, cdf, pdf = reference_score_table()
+    return OracleDiffuser(tab, cdf=cdf, pdf=pdf)
+
+
+def maxabs(a, b):
+    return float((torch.as_tensor(a).double() - torch.as_tensor(b).double()).abs().max())
