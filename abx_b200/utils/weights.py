@@ -47,3 +47,9 @@ def load_seeded_(module, seed=0):
     new = {k: v.to(dtype=sd[k].dtype) for k, v in new.items()}
     module.load_state_dict(new, strict=True)
     return module
+
+
+def np_randn(seed, *shape):
+    """Platform-independent standard-normal float32 tensor (numpy PCG64), for test inputs that are too
+    large to store as fixtures."""
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(size=shape).astype(np.float32))

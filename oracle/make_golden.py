@@ -253,17 +253,18 @@ def gen_ipa():
     model, cfg = _ref_model()
     ipa = model.impl.diffusion_module.ScoreNetwork.attention_module
     from abx.model.quat_affine import quat_to_rot
+    from abx_b200.utils.weights import np_randn
     g = torch.Generator().manual_seed(21)
     B, N = 2, 37
-    x = torch.randn(B, N, 256, generator=g)
-    z = torch.randn(B, N, N, 128, generator=g)
+    x = np_randn(211, B, N, 256)              # regenerated from the seed by the tests (not stored)
+    z = np_randn(212, B, N, N, 128)
     q = torch.randn(B, N, 4, generator=g); q = q / q.norm(dim=-1, keepdim=True)
     trans = torch.randn(B, N, 3, generator=g) * 1.5           # nm units (Å / position_scale)
     mask = torch.ones(B, N)
     mask[1, -5:] = 0
     with torch.no_grad():
         out = ipa(inputs_1d=x, inputs_2d=z, mask=mask, in_rigids=(quat_to_rot(q), trans))
-    save('ipa', x=x, z=z, quat=q, rots=quat_to_rot(q), trans=trans, mask=mask, out=out)
+    save('ipa', quat=q, rots=quat_to_rot(q), trans=trans, mask=mask, out=out)
 
 
 def gen_ipascore():
@@ -271,12 +272,12 @@ def gen_ipascore():
     model, cfg = _ref_model()
     batch = _ref_features()
     B, N = batch['seq'].shape
-    g = torch.Generator().manual_seed(22)
-    rep = {'seq': torch.randn(B, N, 544, generator=g), 'pair': torch.randn(B, N, N, 192, generator=g)}
+    from abx_b200.utils.weights import np_randn
+    rep = {'seq': np_randn(221, B, N, 544), 'pair': np_randn(222, B, N, N, 192)}   # regenerated by the tests
     batch['t'] = torch.tensor([0.7, 0.2])
     with torch.no_grad():
         out = model.impl.diffusion_module.ScoreNetwork(rep, batch)
-    save('ipascore', rep_seq=rep['seq'], rep_pair=rep['pair'], **_batch_arrays(batch),
+    save('ipascore', **_batch_arrays(batch),
          rot_score=out['rot_score'], trans_score=out['trans_score'], rigids=out['rigids'],
          structure_module=out['representations']['structure_module'],
          angles_sin_cos=out['sidechains'][-1]['angles_sin_cos'],
