@@ -1,0 +1,462 @@
+// Invariant Point Attention (abx/model/folding.py:47-132) as a pipeline of sm_100a kernels:
+//
+//   node GEMMs (linear.cu)     x -> [q_scalar | kv_scalar | q_point_local | kv_point_local]      :69-86
+//   ipa_pack_kernel            rigid transform of the points into the global frame, per-head packing :89-93
+//   ipa_pair_bias_kernel       sqrt(1/3) (z W_pair^T + b), head-major [B,H,N,N]  (once per IpaScore) :101-104
+//   ipa_attention_kernel       logits (scalar + point distance + pair bias), mask, softmax,
+//                              attention over scalar / point values, inverse rigid transform, norms :79-123
+//   ipa_pair_aggregate_kernel  o_pair[i,h,:] = sum_j a[h,i,j] z[i,j,:]  — the O(N^2 Cz) HBM stream   :126-127
+//   node GEMM                  final_proj over the 2112-wide feature row                           :130-132
+//
+// Data layout (all fp32): z [B,N,N,128] row-major as the reference holds it; per-head node operands
+// Qdat/Kdat [B,H,N,28] (16 scalar channels + 4 points x 3) and Vdat [B,H,N,40] (16 + 8 points x 3);
+// probabilities and pair bias head-major [B,H,N,N] so that both the attention kernel (fixed h, rows of
+// j) and the aggregation kernel (fixed i, 12 rows of j) read contiguous runs.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace abx {
+
+int launch_linear_f32(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w,
+                      const float* bias, const float* residual, int relu, float* y, int ldy);
+
+constexpr int kH = ABX_IPA_H, kC = ABX_IPA_C, kCz = ABX_IPA_CZ, kFeat = ABX_IPA_FEAT;
+constexpr int kSqk = 16, kSv = 16, kPqk = 4, kPv = 8;
+constexpr int kQK = kSqk + 3 * kPqk;     // 28 floats per (residue, head) on the query/key side
+constexpr int kVD = kSv + 3 * kPv;       // 40 floats per (residue, head) on the value side
+constexpr int kProj = kH * (kSqk + kSqk + kSv) + 3 * kH * (kPqk + kPqk + kPv);   // 1152
+constexpr int kOffKV = kH * kSqk;                   // 192: kv_scalar columns
+constexpr int kOffQP = kOffKV + kH * (kSqk + kSv);  // 576: q_point_local columns
+constexpr int kOffKVP = kOffQP + 3 * kH * kPqk;     // 720: kv_point_local columns
+// feature row: [o_scalar 192 | o_point_local (r n) 288 | o_point_norm 96 | o_pair 1536]
+constexpr int kFeatPt = kH * kSv, kFeatNorm = kFeatPt + 3 * kH * kPv, kFeatPair = kFeatNorm + kH * kPv;
+static_assert(kProj == 1152 && kFeatPair + kH * kCz == kFeat, "IPA geometry");
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {   // streaming read: keep out of L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pack: one thread per (b, n, h).  proj row -> Qdat/Kdat/Vdat with the points moved to the global frame
+// (r3.rigids_apply, r3.py:9-16) and the query scalars pre-multiplied by sqrt(1/(3*16)) (folding.py:59,79).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ipa_pack_kernel(int B, int N, const float* __restrict__ proj,
+                                                       const float* __restrict__ rots, const float* __restrict__ trans,
+                                                       float* __restrict__ Qdat, float* __restrict__ Kdat,
+                                                       float* __restrict__ Vdat) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N * kH) return;
+  const int h = idx % kH, bn = idx / kH, b = bn / N, n = bn % N;
+  const float* row = proj + (size_t)bn * kProj;
+  float R[9], t[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = rots[(size_t)bn * 9 + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t[k] = trans[(size_t)bn * 3 + k];
+  const size_t o = ((size_t)(b * kH + h) * N + n);
+  float* q = Qdat + o * kQK;
+  float* kk = Kdat + o * kQK;
+  float* v = Vdat + o * kVD;
+  const float w_scalar = sqrtf(1.0f / (3.0f * kSqk));
+#pragma unroll
+  for (int c = 0; c < kSqk; ++c) q[c] = row[h * kSqk + c] * w_scalar;
+#pragma unroll
+  for (int c = 0; c < kSqk; ++c) kk[c] = row[kOffKV + h * (kSqk + kSv) + c];
+#pragma unroll
+  for (int c = 0; c < kSv; ++c) v[c] = row[kOffKV + h * (kSqk + kSv) + kSqk + c];
+  auto apply = [&](float lx, float ly, float lz, float* out) {
+    out[0] = t[0] + (R[0] * lx + R[1] * ly + R[2] * lz);
+    out[1] = t[1] + (R[3] * lx + R[4] * ly + R[5] * lz);
+    out[2] = t[2] + (R[6] * lx + R[7] * ly + R[8] * lz);
+  };
+#pragma unroll
+  for (int p = 0; p < kPqk; ++p) {   // channel layout '(r n)', n = (h p)   folding.py:82,91
+    const float* l = row + kOffQP + h * kPqk + p;
+    apply(l[0], l[kH * kPqk], l[2 * kH * kPqk], q + kSqk + 3 * p);
+  }
+#pragma unroll
+  for (int p = 0; p < kPqk + kPv; ++p) {   // per head: 4 key points then 8 value points   folding.py:93
+    const float* l = row + kOffKVP + h * (kPqk + kPv) + p;
+    float* dst = (p < kPqk) ? (kk + kSqk + 3 * p) : (v + kSv + 3 * (p - kPqk));
+    apply(l[0], l[kH * (kPqk + kPv)], l[2 * kH * (kPqk + kPv)], dst);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pair bias: one CTA per (b, i, 64-wide j tile); the z tile is staged in shared memory (row stride 132
+// floats: conflict-free float4 reads with lanes on consecutive j), thread = (j, group of 3 heads).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBiasJ = 64, kZld = kCz + 4;
+
+__global__ void __launch_bounds__(256) ipa_pair_bias_kernel(int N, const float* __restrict__ z,
+                                                            const float* __restrict__ w_pair,
+                                                            const float* __restrict__ b_pair, float* __restrict__ bias) {
+  __shared__ __align__(16) float zs[kBiasJ * kZld];
+  __shared__ __align__(16) float ws[kH * kCz];
+  const int j0 = blockIdx.x * kBiasJ, i = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < kH * kCz / 4; k += 256)
+    reinterpret_cast<float4*>(ws)[k] = __ldg(reinterpret_cast<const float4*>(w_pair) + k);
+  const float4* zrow = reinterpret_cast<const float4*>(z + (((size_t)b * N + i) * N + j0) * kCz);
+  const int nj = min(kBiasJ, N - j0);
+  for (int k = tid; k < nj * (kCz / 4); k += 256) {
+    int jj = k / (kCz / 4), c4 = k % (kCz / 4);
+    *reinterpret_cast<float4*>(&zs[jj * kZld + 4 * c4]) = ldg_stream(zrow + k);
+  }
+  __syncthreads();
+  const int jj = tid % kBiasJ, hg = tid / kBiasJ;     // heads 3*hg .. 3*hg+2
+  if (jj >= nj) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 8
+  for (int c = 0; c < kCz; c += 4) {
+    float4 zv = *reinterpret_cast<const float4*>(&zs[jj * kZld + c]);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      float4 wv = *reinterpret_cast<const float4*>(&ws[(3 * hg + u) * kCz + c]);
+      acc[u] = fmaf(zv.x, wv.x, acc[u]); acc[u] = fmaf(zv.y, wv.y, acc[u]);
+      acc[u] = fmaf(zv.z, wv.z, acc[u]); acc[u] = fmaf(zv.w, wv.w, acc[u]);
+    }
+  }
+  const float w_pair_scale = sqrtf(1.0f / 3.0f);
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    int h = 3 * hg + u;
+    bias[(((size_t)b * kH + h) * N + i) * N + j0 + jj] = w_pair_scale * (acc[u] + __ldg(b_pair + h));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// attention: one CTA per (b, h, 32 query rows).  The 32 x N logit tile lives in shared memory (row
+// stride odd -> conflict-free with lanes on rows), so the softmax is the exact two-pass one.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRows = 32, kAttnThreads = 256, kAttnWarps = kAttnThreads / 32, kOld = kVD + 1;
+
+__host__ __device__ inline int attn_ld(int N) { return N | 1; }
+__host__ inline size_t attn_smem_bytes(int N) {
+  size_t a = (size_t)kRows * attn_ld(N), b = (size_t)kAttnWarps * kRows * kOld;
+  return (a > b ? a : b) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
+    int N, const float* __restrict__ Qdat, const float* __restrict__ Kdat, const float* __restrict__ Vdat,
+    const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
+    const float* __restrict__ trans, const float* __restrict__ point_weights, float* __restrict__ probs,
+    float* __restrict__ feats) {
+  extern __shared__ __align__(16) float S[];
+  __shared__ float O[kRows][kOld];
+  const int ld = attn_ld(N);
+  const int i0 = blockIdx.x * kRows, h = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const size_t bh = (size_t)b * kH + h;
+
+  // 1. pair-bias tile -> S (coalesced along j)
+  const float* bias_bh = bias + bh * N * N;
+  for (int r = wid; r < kRows; r += kAttnWarps) {
+    int i = i0 + r;
+    if (i < N)
+      for (int j = lane; j < N; j += 32) S[r * ld + j] = __ldg(bias_bh + (size_t)i * N + j);
+  }
+  __syncthreads();
+
+  // 2. logits: lane = query row, warps stride over keys (key operands are warp-uniform loads)
+  {
+    const int i = i0 + lane;
+    const bool row_ok = i < N;
+    float q[kQK];
+    if (row_ok) {
+      const float4* qp = reinterpret_cast<const float4*>(Qdat + (bh * N + i) * kQK);
+#pragma unroll
+      for (int k = 0; k < kQK / 4; ++k) { float4 v = __ldg(qp + k); q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kQK; ++k) q[k] = 0.f;
+    }
+    const float pw = __ldg(point_weights + h);
+    const float gamma = (pw > 20.f) ? pw : log1pf(expf(pw));                    // F.softplus  folding.py:96
+    const float coef = -0.5f * sqrtf(1.0f / (3.0f * kPqk * 9.0f / 2.0f)) * gamma;   // -1/2 w_point gamma  :97-99
+    const float mi = row_ok ? __ldg(mask + (size_t)b * N + i) : 0.f;
+    const float4* Kbh = reinterpret_cast<const float4*>(Kdat + bh * N * kQK);
+    for (int j = wid; j < N; j += kAttnWarps) {
+      float k[kQK];
+#pragma unroll
+      for (int u = 0; u < kQK / 4; ++u) { float4 v = __ldg(Kbh + (size_t)j * (kQK / 4) + u); k[4 * u] = v.x; k[4 * u + 1] = v.y; k[4 * u + 2] = v.z; k[4 * u + 3] = v.w; }
+      float dot = 0.f, d2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kSqk; ++c) dot = fmaf(q[c], k[c], dot);
+#pragma unroll
+      for (int c = kSqk; c < kQK; ++c) { float d = q[c] - k[c]; d2 = fmaf(d, d, d2); }
+      if (row_ok) {
+        float lg = (dot + coef * d2) + S[lane * ld + j];
+        bool ok = (mi * __ldg(mask + (size_t)b * N + j)) != 0.f;                // mask_2d  folding.py:106-109
+        S[lane * ld + j] = ok ? lg : -FLT_MAX;
+      }
+    }
+  }
+  __syncthreads();
+
+  // 3. softmax over j, one warp per row; probabilities go to global (for the pair aggregation) and stay in S
+  for (int r = wid; r < kRows; r += kAttnWarps) {
+    int i = i0 + r;
+    if (i >= N) continue;
+    float* Sr = S + r * ld;
+    float mx = -FLT_MAX;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, Sr[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) { float e = expf(Sr[j] - mx); Sr[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    float* pr = probs + (bh * N + i) * N;
+    for (int j = lane; j < N; j += 32) { float p = Sr[j] / sum; Sr[j] = p; pr[j] = p; }
+  }
+  __syncthreads();
+
+  // 4. scalar + point values: lane = row, warps split the keys, then an 8-way reduction through smem
+  {
+    float acc[kVD];
+#pragma unroll
+    for (int d = 0; d < kVD; ++d) acc[d] = 0.f;
+    const float4* Vbh = reinterpret_cast<const float4*>(Vdat + bh * N * kVD);
+    for (int j = wid; j < N; j += kAttnWarps) {
+      const float s = S[lane * ld + j];
+#pragma unroll
+      for (int u = 0; u < kVD / 4; ++u) {
+        float4 v = __ldg(Vbh + (size_t)j * (kVD / 4) + u);
+        acc[4 * u] = fmaf(s, v.x, acc[4 * u]); acc[4 * u + 1] = fmaf(s, v.y, acc[4 * u + 1]);
+        acc[4 * u + 2] = fmaf(s, v.z, acc[4 * u + 2]); acc[4 * u + 3] = fmaf(s, v.w, acc[4 * u + 3]);
+      }
+    }
+    __syncthreads();                       // everyone is done reading S; reuse it for the partial sums
+    float* P = S + (size_t)(wid * kRows + lane) * kOld;
+#pragma unroll
+    for (int d = 0; d < kVD; ++d) P[d] = acc[d];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < kRows * kVD; o += kAttnThreads) {
+    int r = o / kVD, d = o % kVD;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) v += S[(size_t)(w * kRows + r) * kOld + d];
+    O[r][d] = v;
+  }
+  __syncthreads();
+
+  // 5. write the node features of these rows
+  for (int o = threadIdx.x; o < kRows * kSv; o += kAttnThreads) {
+    int r = o / kSv, c = o % kSv, i = i0 + r;
+    if (i < N) feats[((size_t)b * N + i) * kFeat + h * kSv + c] = O[r][c];      // 'b i h c -> b i (h c)'
+  }
+  {
+    int r = threadIdx.x / kPv, p = threadIdx.x % kPv, i = i0 + r;               // 32 rows x 8 points = 256 threads
+    if (i < N) {
+      const size_t bn = (size_t)b * N + i;
+      float R[9], t[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = __ldg(rots + bn * 9 + k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] = __ldg(trans + bn * 3 + k);
+      // invert_rigids (r3.py:54-59): R^T, -(R^T t); then rigids_apply  folding.py:121
+      float it[3], g[3], l[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) it[k] = -(R[k] * t[0] + R[3 + k] * t[1] + R[6 + k] * t[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g[k] = O[r][kSv + 3 * p + k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) l[k] = it[k] + (R[k] * g[0] + R[3 + k] * g[1] + R[6 + k] * g[2]);
+      float* f = feats + bn * kFeat;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) f[kFeatPt + k * (kH * kPv) + h * kPv + p] = l[k];      // '(r n)'  folding.py:122
+      f[kFeatNorm + h * kPv + p] = sqrtf(l[0] * l[0] + l[1] * l[1] + l[2] * l[2] + 1e-8f);   // :123
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pair aggregation: o_pair[b,i,h,:] = sum_j a[b,h,i,j] z[b,i,j,:].  One CTA per (b, i): the 12 x N
+// probabilities of the row are staged (transposed to [j][12]) in shared memory, each warp streams
+// every 4th z[i,j,:] row straight from HBM into registers (one 16-byte load per lane covers the 512 B
+// row), 48 FMAs per load; the four partial sums are reduced through shared memory.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kAggThreads = 128, kAggWarps = kAggThreads / 32, kAggUnroll = 4;
+
+__global__ void __launch_bounds__(kAggThreads) ipa_pair_aggregate_kernel(int N, const float* __restrict__ z,
+                                                                         const float* __restrict__ probs,
+                                                                         float* __restrict__ feats) {
+  extern __shared__ __align__(16) float A[];        // [N][12] probabilities, then reused for the reduction
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int h = wid; h < kH; h += kAggWarps) {
+    const float* pr = probs + (((size_t)b * kH + h) * N + i) * N;
+    for (int j = lane; j < N; j += 32) A[j * kH + h] = __ldg(pr + j);
+  }
+  __syncthreads();
+
+  float acc[kH][4];
+#pragma unroll
+  for (int h = 0; h < kH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+  const float4* zrow = reinterpret_cast<const float4*>(z + ((size_t)b * N + i) * N * kCz) + lane;
+  for (int j0 = wid; j0 < N; j0 += kAggWarps * kAggUnroll) {
+    float4 zv[kAggUnroll];
+#pragma unroll
+    for (int u = 0; u < kAggUnroll; ++u) {
+      int j = j0 + u * kAggWarps;
+      zv[u] = (j < N) ? ldg_stream(zrow + (size_t)j * (kCz / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kAggUnroll; ++u) {
+      int j = j0 + u * kAggWarps;
+      if (j < N) {
+        const float4* ap = reinterpret_cast<const float4*>(A + j * kH);
+        float a[kH];
+#pragma unroll
+        for (int k = 0; k < kH / 4; ++k) { float4 v = ap[k]; a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w; }
+#pragma unroll
+        for (int h = 0; h < kH; ++h) {
+          acc[h][0] = fmaf(a[h], zv[u].x, acc[h][0]); acc[h][1] = fmaf(a[h], zv[u].y, acc[h][1]);
+          acc[h][2] = fmaf(a[h], zv[u].z, acc[h][2]); acc[h][3] = fmaf(a[h], zv[u].w, acc[h][3]);
+        }
+      }
+    }
+  }
+  __syncthreads();                                   // done with A; reuse as red[warp][h][128]
+  float4* red = reinterpret_cast<float4*>(A);
+#pragma unroll
+  for (int h = 0; h < kH; ++h)
+    red[(wid * kH + h) * (kCz / 4) + lane] = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+  __syncthreads();
+  float4* out = reinterpret_cast<float4*>(feats + ((size_t)b * N + i) * kFeat + kFeatPair);   // 'b i h c -> b i (h c)'
+  for (int o = threadIdx.x; o < kH * kCz / 4; o += kAggThreads) {
+    float4 s = red[o];
+#pragma unroll
+    for (int w = 1; w < kAggWarps; ++w) {
+      float4 v = red[w * kH * (kCz / 4) + o];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    out[o] = s;
+  }
+}
+
+__host__ inline size_t agg_smem_bytes(int N) {
+  size_t a = (size_t)N * kH, b = (size_t)kAggWarps * kH * kCz;
+  return (a > b ? a : b) * sizeof(float);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct IpaWorkspace {
+  float *proj, *Qdat, *Kdat, *Vdat, *probs, *feats, *bias;
+  size_t total;
+};
+
+static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_feats) {
+  IpaWorkspace w;
+  size_t off = 0;
+  char* p = reinterpret_cast<char*>(base);
+  auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(p + off); off += align_up(floats * sizeof(float)); return r; };
+  const size_t bn = (size_t)B * N;
+  w.proj = take(bn * kProj);
+  w.Qdat = take(bn * kH * kQK);
+  w.Kdat = take(bn * kH * kQK);
+  w.Vdat = take(bn * kH * kVD);
+  w.probs = take(bn * kH * N);
+  w.feats = with_feats ? take(bn * kFeat) : nullptr;
+  w.bias = with_bias ? take(bn * kH * N) : nullptr;
+  w.total = off;
+  return w;
+}
+
+static int ipa_features(cudaStream_t s, int B, int N, const float* x, const float* z, const float* mask,
+                        const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
+                        float* feats, const IpaWorkspace& ws) {
+  const int M = B * N;
+  int rc;
+  // node projections (folding.py:69-86): four Linear layers into one [M, 1152] buffer
+  if ((rc = launch_linear_f32(s, M, kH * kSqk, kC, x, kC, w->w_q_scalar, w->b_q_scalar, nullptr, 0, ws.proj, kProj))) return rc;
+  if ((rc = launch_linear_f32(s, M, kH * (kSqk + kSv), kC, x, kC, w->w_kv_scalar, w->b_kv_scalar, nullptr, 0, ws.proj + kOffKV, kProj))) return rc;
+  if ((rc = launch_linear_f32(s, M, 3 * kH * kPqk, kC, x, kC, w->w_q_point, w->b_q_point, nullptr, 0, ws.proj + kOffQP, kProj))) return rc;
+  if ((rc = launch_linear_f32(s, M, 3 * kH * (kPqk + kPv), kC, x, kC, w->w_kv_point, w->b_kv_point, nullptr, 0, ws.proj + kOffKVP, kProj))) return rc;
+  ipa_pack_kernel<<<ceil_div(M * kH, 128), 128, 0, s>>>(B, N, ws.proj, rots, trans, ws.Qdat, ws.Kdat, ws.Vdat);
+  count_launch();
+  if ((rc = check_launch("ipa_pack_kernel"))) return rc;
+
+  if (pair_bias == nullptr) {
+    ipa_pair_bias_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), 256, 0, s>>>(N, z, w->w_pair, w->b_pair, ws.bias);
+    count_launch();
+    if ((rc = check_launch("ipa_pair_bias_kernel"))) return rc;
+    pair_bias = ws.bias;
+  }
+
+  const size_t asmem = attn_smem_bytes(N);
+  if (asmem > 48 * 1024)
+    ABX_CUDA(cudaFuncSetAttribute(ipa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+  ipa_attention_kernel<<<dim3(ceil_div(N, kRows), kH, B), kAttnThreads, asmem, s>>>(
+      N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, feats);
+  count_launch();
+  if ((rc = check_launch("ipa_attention_kernel"))) return rc;
+
+  const size_t gsmem = agg_smem_bytes(N);
+  if (gsmem > 48 * 1024)
+    ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+  ipa_pair_aggregate_kernel<<<dim3(N, B), kAggThreads, gsmem, s>>>(N, z, ws.probs, feats);
+  count_launch();
+  return check_launch("ipa_pair_aggregate_kernel");
+}
+
+static int ipa_check(const char* fn, int B, int N, const void* x, const void* z, const void* mask, const void* rots,
+                     const void* trans, const abx_ipa_weights* w) {
+  ABX_REQUIRE(B > 0 && N > 0 && x && z && mask && rots && trans && w, "%s: bad shape or null argument", fn);
+  ABX_REQUIRE(N <= 1536, "%s: N=%d exceeds the supported maximum of 1536 residues", fn, N);
+  ABX_REQUIRE(w->w_q_scalar && w->w_kv_scalar && w->w_q_point && w->w_kv_point && w->w_pair && w->b_pair &&
+                  w->point_weights && w->w_final, "%s: null weight pointer", fn);
+  ABX_REQUIRE((uintptr_t)z % 16 == 0 && (uintptr_t)x % 16 == 0, "%s: x and z must be 16-byte aligned", fn);
+  return ABX_OK;
+}
+
+}  // namespace abx
+
+using namespace abx;
+
+extern "C" size_t abx_ipa_workspace_bytes(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  return carve(nullptr, B, N, true, true).total;
+}
+
+extern "C" int abx_ipa_pair_bias(void* stream, int B, int N, const float* z, const float* w_pair, const float* b_pair,
+                                 float* pair_bias) {
+  ABX_REQUIRE(B > 0 && N > 0 && z && w_pair && b_pair && pair_bias, "abx_ipa_pair_bias: bad shape or null argument");
+  ABX_REQUIRE((uintptr_t)z % 16 == 0 && (uintptr_t)w_pair % 16 == 0, "abx_ipa_pair_bias: z and w_pair must be 16-byte aligned");
+  ipa_pair_bias_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), 256, 0, (cudaStream_t)stream>>>(N, z, w_pair, b_pair, pair_bias);
+  count_launch();
+  return check_launch("ipa_pair_bias_kernel");
+}
+
+extern "C" int abx_ipa_attention_features(void* stream, int B, int N, const float* x, const float* z, const float* mask,
+                                          const float* rots, const float* trans, const abx_ipa_weights* w,
+                                          const float* pair_bias, float* feats, void* workspace, size_t workspace_bytes) {
+  int rc = ipa_check("abx_ipa_attention_features", B, N, x, z, mask, rots, trans, w);
+  if (rc) return rc;
+  ABX_REQUIRE(feats && workspace, "abx_ipa_attention_features: null output or workspace");
+  IpaWorkspace ws = carve(workspace, B, N, pair_bias == nullptr, false);
+  ABX_REQUIRE(workspace_bytes >= ws.total, "abx_ipa_attention_features: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+  return ipa_features((cudaStream_t)stream, B, N, x, z, mask, rots, trans, w, pair_bias, feats, ws);
+}
+
+extern "C" int abx_ipa_forward(void* stream, int B, int N, const float* x, const float* z, const float* mask,
+                               const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
+                               const float* residual, float* out, void* workspace, size_t workspace_bytes) {
+  int rc = ipa_check("abx_ipa_forward", B, N, x, z, mask, rots, trans, w);
+  if (rc) return rc;
+  ABX_REQUIRE(out && workspace, "abx_ipa_forward: null output or workspace");
+  IpaWorkspace ws = carve(workspace, B, N, pair_bias == nullptr, true);
+  ABX_REQUIRE(workspace_bytes >= ws.total, "abx_ipa_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = ipa_features(s, B, N, x, z, mask, rots, trans, w, pair_bias, ws.feats, ws))) return rc;
+  // final_proj (folding.py:130-132) with the residual of score_network.py:128 fused into the epilogue
+  return launch_linear_f32(s, B * N, kC, kFeat, ws.feats, kFeat, w->w_final, w->b_final, residual, 0, out, kC);
+}

@@ -1,0 +1,65 @@
+"""Small building blocks shared by the model modules (reference: abx/model/common_modules.py)."""
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import LayerNorm  # noqa: F401  (re-exported, as the reference does)
+
+
+class ConfigView(dict):
+    """Attribute access over a (nested) dict; accepts ml_collections.ConfigDict-like objects too."""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+        return ConfigView(v) if isinstance(v, dict) else v
+
+    def get(self, k, default=None):
+        v = dict.get(self, k, default)
+        return ConfigView(v) if isinstance(v, dict) else v
+
+
+def as_config(c):
+    if isinstance(c, ConfigView):
+        return c
+    if isinstance(c, dict):
+        return ConfigView(c)
+    if hasattr(c, 'to_dict'):
+        return ConfigView(c.to_dict())
+    return c
+
+
+def Linear(input_dim, output_dim, init='linear', bias=True, config=None):
+    """nn.Linear with the AF2-style initialisers of common_modules.py:11-38."""
+    assert init in ('gate', 'final', 'attn', 'relu', 'linear')
+    layer = nn.Linear(input_dim, output_dim, bias=bias)
+    with torch.no_grad():
+        if init in ('gate', 'final'):
+            layer.weight.zero_()
+        elif init == 'attn':
+            nn.init.xavier_uniform_(layer.weight)
+        else:
+            std = np.sqrt((2.0 if init == 'relu' else 1.0) / input_dim) / 0.87962566103423978
+            nn.init.trunc_normal_(layer.weight, mean=0.0, std=std)
+        if bias:
+            layer.bias.fill_(1.0 if init == 'gate' else 0.0)
+    return layer
+
+
+def pseudo_beta_fn_v2(aatype, all_atom_positions, all_atom_masks=None):
+    """common_modules.py:61-83: ideal C-beta from N, CA, C (atom indices 0, 1, 2)."""
+    n, ca, c = all_atom_positions[..., 0, :], all_atom_positions[..., 1, :], all_atom_positions[..., 2, :]
+    b, cc = ca - n, c - ca
+    a = torch.cross(b, cc, dim=-1)
+    cb = -0.58273431 * a + 0.56802827 * b - 0.54067466 * cc + ca
+    if all_atom_masks is not None:
+        return cb, all_atom_masks[..., 1]
+    return cb
+
+
+def dgram_from_positions(positions, num_bins, min_bin, max_bin):
+    """common_modules.py:107-120: index of the squared-distance bin, [B,N,N] int64."""
+    breaks = torch.linspace(min_bin, max_bin, steps=num_bins - 1, device=positions.device) ** 2
+    d2 = torch.sum((positions[:, :, None] - positions[:, None]) ** 2, dim=-1)
+    return torch.bucketize(d2, breaks, right=False)      # == sum(d2 > breaks)

@@ -1,0 +1,111 @@
+"""`InvariantPointAttention` — the reference's abx/model/folding.py:23-132 module (same constructor, same
+parameter names/shapes, same forward signature) executing on the sm_100a kernels behind
+`abx_ipa_forward` (include/abx_b200.h).  There is no PyTorch fallback: CPU tensors raise.
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from abx_b200 import lib
+from abx_b200.model.common_modules import Linear, as_config
+
+
+class Workspace:
+    """Grow-only per-device scratch buffer handed to the C-ABI calls (kernels never allocate)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, nbytes, device):
+        key = str(device)
+        b = self._buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self._buf[key] = b
+        return b
+
+
+WORKSPACE = Workspace()
+
+
+class InvariantPointAttention(nn.Module):
+
+    def __init__(self, config, num_in_pair_channel, dist_epsilon=1e-8):
+        super().__init__()
+        c = as_config(config)
+        self.proj_q_scalar = Linear(c.num_channel, c.num_head * c.num_scalar_qk, init='attn')
+        self.proj_kv_scalar = Linear(c.num_channel, c.num_head * (c.num_scalar_v + c.num_scalar_qk), init='attn')
+        self.proj_q_point_local = Linear(c.num_channel, 3 * c.num_head * c.num_point_qk, init='attn')
+        self.proj_kv_point_local = Linear(c.num_channel, 3 * c.num_head * (c.num_point_v + c.num_point_qk), init='attn')
+        self.proj_pair = Linear(num_in_pair_channel, c.num_head, init='attn')
+        self.trainable_point_weights = nn.Parameter(torch.log(torch.exp(torch.full((c.num_head,), 1.)) - 1.))
+        self.final_proj = Linear(c.num_head * (c.num_scalar_v + num_in_pair_channel + c.num_point_v * (3 + 1)),
+                                 c.num_channel, init='final')
+        self.config = c
+        self.dist_epsilon = dist_epsilon
+        geom = (c.num_head, c.num_channel, c.num_scalar_qk, c.num_scalar_v, c.num_point_qk, c.num_point_v,
+                num_in_pair_channel)
+        if geom != (12, 256, 16, 16, 4, 8, 128) or dist_epsilon != 1e-8:
+            raise NotImplementedError(f'the sm_100a IPA kernels are specialised for the shipped AbX geometry '
+                                      f'(config_model.json:107-124); got {geom}')
+        self._lib = lib.load()
+        self._wstruct = None
+
+    def _weights(self):
+        """abx_ipa_weights over the live parameter storage (rebuilt if parameters were moved/reloaded)."""
+        ps = [self.proj_q_scalar.weight, self.proj_q_scalar.bias, self.proj_kv_scalar.weight, self.proj_kv_scalar.bias,
+              self.proj_q_point_local.weight, self.proj_q_point_local.bias, self.proj_kv_point_local.weight,
+              self.proj_kv_point_local.bias, self.proj_pair.weight, self.proj_pair.bias, self.trainable_point_weights,
+              self.final_proj.weight, self.final_proj.bias]
+        key = tuple(p.data_ptr() for p in ps)
+        if self._wstruct is None or self._wstruct[0] != key:
+            self._wstruct = (key, lib.IpaWeights(*(lib.ptr(p.detach(), torch.float32) for p in ps)))
+        return self._wstruct[1]
+
+    def pair_bias(self, inputs_2d):
+        """sqrt(1/3) * proj_pair(z), head-major [B,H,N,N] (folding.py:101-104) — reusable across calls that
+        share `inputs_2d` and weights (the 8 iterations of IpaScore)."""
+        B, N = inputs_2d.shape[:2]
+        z = inputs_2d.float().contiguous()
+        out = torch.empty(B, self.config.num_head, N, N, device=z.device, dtype=torch.float32)
+        with torch.cuda.device(z.device):
+            lib.check(self._lib.abx_ipa_pair_bias(lib.stream(), B, N, lib.ptr(z), lib.ptr(self.proj_pair.weight.detach()),
+                                                  lib.ptr(self.proj_pair.bias.detach()), lib.ptr(out)))
+        return out
+
+    def forward(self, inputs_1d, inputs_2d, mask, in_rigids, pair_bias=None, residual=None):
+        """Reference signature plus two optional fusions: `pair_bias` (from `pair_bias()`), `residual`
+        (added in the final_proj epilogue, score_network.py:128)."""
+        B, N, _ = inputs_1d.shape
+        rots, trans = in_rigids
+        dev = inputs_1d.device
+        x = inputs_1d.float().contiguous()
+        z = inputs_2d.float().contiguous()
+        m = mask.to(torch.float32).contiguous()
+        rots = rots.float().contiguous()
+        trans = trans.float().contiguous()
+        out = torch.empty(B, N, self.config.num_channel, device=dev, dtype=torch.float32)
+        nbytes = self._lib.abx_ipa_workspace_bytes(B, N)
+        ws = WORKSPACE.get(nbytes, dev)
+        with torch.cuda.device(dev):
+            lib.check(self._lib.abx_ipa_forward(
+                lib.stream(), B, N, lib.ptr(x), lib.ptr(z), lib.ptr(m), lib.ptr(rots), lib.ptr(trans),
+                ctypes.byref(self._weights()), lib.ptr(pair_bias), lib.ptr(residual), lib.ptr(out), lib.ptr(ws), nbytes))
+        return out
+
+    def attention_features(self, inputs_1d, inputs_2d, mask, in_rigids, pair_bias=None):
+        """The 2112-wide feature row fed to final_proj (folding.py:114-128), for tests and profiling."""
+        B, N, _ = inputs_1d.shape
+        rots, trans = in_rigids
+        dev = inputs_1d.device
+        feats = torch.empty(B, N, 2112, device=dev, dtype=torch.float32)
+        nbytes = self._lib.abx_ipa_workspace_bytes(B, N)
+        ws = WORKSPACE.get(nbytes, dev)
+        with torch.cuda.device(dev):
+            lib.check(self._lib.abx_ipa_attention_features(
+                lib.stream(), B, N, lib.ptr(inputs_1d.float().contiguous()), lib.ptr(inputs_2d.float().contiguous()),
+                lib.ptr(mask.to(torch.float32).contiguous()), lib.ptr(rots.float().contiguous()),
+                lib.ptr(trans.float().contiguous()), ctypes.byref(self._weights()), lib.ptr(pair_bias), lib.ptr(feats),
+                lib.ptr(ws), nbytes))
+        return feats

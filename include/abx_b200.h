@@ -1,0 +1,164 @@
+/* abx_b200 — C ABI of the B200 (sm_100a) kernels behind AbX's reverse-diffusion sampling path.
+ *
+ * The reference (CarbonMatrixLab/AbX) is pure Python/PyTorch and has no FFI of its own, so the
+ * drop-in boundary is its Python API; this library sits directly underneath the
+ * Python classes that mirror that API (abx_b200/diffuser/*.py, abx_b200/model/*.py).  Every entry
+ * point names the reference code (file:line under the AbX checkout) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is DEVICE memory unless stated otherwise
+ *   - the caller owns every buffer, including outputs and workspaces (kernels never allocate)
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no internal syncs
+ *   - tensors are contiguous row-major with the shapes given per function
+ *   - return value: 0 = ok, non-zero = error (message via abx_last_error()); never throws
+ *   - no global mutable state besides the launch counter and the last-error string (thread-local)
+ */
+#ifndef ABX_B200_H_
+#define ABX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABX_OK 0
+#define ABX_ERR_INVALID 1   /* bad argument (shape, null pointer, workspace too small) */
+#define ABX_ERR_CUDA 2      /* a CUDA runtime call failed */
+
+/* ---- library -------------------------------------------------------------------------------- */
+const char* abx_last_error(void);          /* message of the last failing call on this thread   */
+int abx_version(void);                     /* ABI version, bumps on any signature change        */
+uint64_t abx_launch_count(void);           /* kernels launched by this library since load/reset */
+void abx_reset_launch_count(void);
+/* ABI checks for a device with compute capability 10.x; fills sm count.  Host call. */
+int abx_device_check(int device, int* sm_count);
+
+/* ---- SE(3) / categorical diffusers ---------------------------------------------------------- */
+/* Scalars of the noise schedules, computed on the HOST by the Python layer exactly as torch does
+ * (float32 0-d tensors promoted against t), so device arithmetic matches the reference bit for bit
+ * in the t-dependent factors.  diffuser/so3_diffuser.py:198-216, r3_diffuser.py:29-46,150-164. */
+typedef struct {
+  double so3_exp_max;      /* (double)float32(exp(max_sigma))                                   */
+  double so3_exp_min;      /* (double)float32(exp(min_sigma))                                   */
+  double so3_g2_coef;      /* (double)float32(2*(exp(max_sigma)-exp(min_sigma)))                */
+  double r3_min_b;         /* (double)float32(min_b)                                            */
+  double r3_delta_b;       /* (double)float32(max_b-min_b)                                      */
+  double r3_coord_scale;   /* (double)float32(coordinate_scaling)                               */
+  double seq_rate;         /* CTMC off-diagonal rate (rate_const)                               */
+  int num_sigma;           /* rows of the IGSO(3) tables                                        */
+  int num_omega;           /* columns of the IGSO(3) tables                                     */
+} abx_diffuser_consts;
+
+/* rot_score/trans_score of a predicted x0 — replaces FullDiffuser.calc_quat_score
+ * (diffuser/full_diffuser.py:135-142 -> quat_affine.py:76-131,234-238 -> so3_diffuser.py:264-297,
+ * cached-table branch) and FullDiffuser.calc_trans_score (full_diffuser.py:131-133 ->
+ * r3_diffuser.py:158-164).
+ *   quat_t, quat_0 [B,N,4] f32; trans_t, trans_0 [B,N,3] f32 (Angstrom); t [B] f64
+ *   t_is_f32: the reference was handed a float32 t (warm-up call, inference.py:210): sigma(t) and
+ *             the translation score are then evaluated in float32
+ *   score_norms [num_sigma,num_omega] f32; discrete_sigma [num_sigma] f32; discrete_omega [num_omega] f32
+ *   rot_score [B,N,3] f32 (may be NULL);  trans_score [B,N,3] f64 (f32 when t_is_f32; may be NULL) */
+int abx_se3_scores(void* stream, int B, int N, const abx_diffuser_consts* c,
+                   const float* quat_t, const float* quat_0, const float* trans_t, const float* trans_0,
+                   const double* t, int t_is_f32,
+                   const float* score_norms, const float* discrete_sigma, const float* discrete_omega,
+                   float* rot_score, void* trans_score);
+
+/* SO3Diffuser.score on a rotation vector (so3_diffuser.py:264-297, cached branch), used by
+ * FullDiffuser.score / forward_marginal.   rotvec [B,N,3] f32 -> rot_score [B,N,3] f32 */
+int abx_so3_score_rotvec(void* stream, int B, int N, const abx_diffuser_consts* c, const float* rotvec,
+                         const double* t, int t_is_f32, const float* score_norms, const float* discrete_sigma,
+                         const float* discrete_omega, float* rot_score);
+
+/* Live (uncached) IGSO(3) score: the truncated character series evaluated per residue, one warp per
+ * residue with warp-shuffle reductions — so3_diffuser.py:72-112 + :290-295 (use_cached_score=False).
+ *   rotvec [B,N,3] f32 -> rot_score [B,N,3] f32;  L = series length (reference: 1000) */
+int abx_igso3_score_series(void* stream, int B, int N, const abx_diffuser_consts* c, const float* rotvec,
+                           const double* t, int t_is_f32, const float* discrete_sigma, int L, float* rot_score);
+
+/* Poisson rates of the categorical tau-leap, rate*dt — discrete_diffuser.py:130-179 (softmax,
+ * transition :53-67, reverse rates).   seq_t [B,N] i64; logits [B,N,20] f32; t [B] f64; dt scalar
+ *   rate_dt [B,N,20] f32 (the tensor the reference hands to torch.poisson) */
+int abx_seq_reverse_rates(void* stream, int B, int N, const abx_diffuser_consts* c, const int64_t* seq_t,
+                          const float* logits, const double* t, double dt, float* rate_dt);
+
+/* One Euler-Maruyama reverse step on SE(3)^N x {0..19}^N — replaces FullDiffuser.reverse
+ * (full_diffuser.py:174-227): so3_diffuser.py:328-361 (geodesic step), r3_diffuser.py:110-148
+ * (VP-SDE step incl. the g*dt*z noise term and centre of mass over all N), discrete_diffuser.py:181-190
+ * (apply jumps), masking in rotvec space (:219-225), _assemble_rigid (:20-26).
+ *   rigid_t [B,N,7] (f32 or f64: rigid_is_f64) = [qw,qx,qy,qz,tx,ty,tz]; seq_t [B,N] i64
+ *   rot_score [B,N,3] f32; trans_score [B,N,3] f64; diffuse_mask [B,N] i32 (NULL = all ones)
+ *   z_rot, z_trans [B,N,3] f32 (the two randn draws, reference order); jumps [B,N,20] f32 (Poisson draw)
+ *   flags: bit0 diffuse_rot, bit1 diffuse_trans, bit2 diffuse_seq, bit3 center
+ *   rigids_out [B,N,7] f64; seq_out [B,N] i64.  One CTA per batch element. */
+int abx_se3_reverse_step(void* stream, int B, int N, const abx_diffuser_consts* c,
+                         const void* rigid_t, int rigid_is_f64, const int64_t* seq_t,
+                         const float* rot_score, const double* trans_score, const int32_t* diffuse_mask,
+                         const double* t, double dt_f32, double sqrt_dt_f32, double noise_scale,
+                         const float* z_rot, const float* z_trans, const float* jumps, int flags,
+                         double* rigids_out, int64_t* seq_out);
+
+/* IGSO(3) tables (pdf, cdf, score norms over a sigma x omega grid) — replaces the cache build in
+ * SO3Diffuser.__init__ (so3_diffuser.py:150-166; igso3_expansion :15-49, density :52-69, score :72-112).
+ *   discrete_sigma [num_sigma] f32, discrete_omega [num_omega] f32 -> three [num_sigma,num_omega] f32 */
+int abx_igso3_build_tables(void* stream, int num_sigma, int num_omega, int L, const float* discrete_sigma,
+                           const float* discrete_omega, float* pdf, float* cdf, float* score_norms);
+
+/* ---- dense node GEMM ------------------------------------------------------------------------- */
+/* y[M,Nout] = act(x[M,K] @ w[Nout,K]^T + bias) (+ residual) — torch.nn.Linear semantics
+ * (abx/model/common_modules.py:11-59).  fp32 in/out, fp32-accurate accumulation.
+ *   bias, residual may be NULL; relu: 0/1; ldx/ldy: row strides in elements (>= K / >= Nout). */
+int abx_linear_f32(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w,
+                   const float* bias, const float* residual, int relu, float* y, int ldy);
+
+/* ---- Invariant Point Attention ---------------------------------------------------------------- */
+/* Weights of abx.model.folding.InvariantPointAttention (folding.py:23-45), reference state_dict
+ * layout (out_features x in_features, row-major). */
+typedef struct {
+  const float* w_q_scalar;  const float* b_q_scalar;    /* [H*16, C], [H*16]        proj_q_scalar       */
+  const float* w_kv_scalar; const float* b_kv_scalar;   /* [H*32, C], [H*32]        proj_kv_scalar      */
+  const float* w_q_point;   const float* b_q_point;     /* [3*H*4, C], [3*H*4]      proj_q_point_local  */
+  const float* w_kv_point;  const float* b_kv_point;    /* [3*H*12, C], [3*H*12]    proj_kv_point_local */
+  const float* w_pair;      const float* b_pair;        /* [H, Cz], [H]             proj_pair           */
+  const float* point_weights;                           /* [H]                      trainable_point_weights */
+  const float* w_final;     const float* b_final;       /* [C, H*(16+8*4+Cz)], [C]  final_proj          */
+} abx_ipa_weights;
+
+/* Geometry of the supported configuration (config/config_model.json:107-124): H=12 heads, 16 scalar
+ * qk/v channels, 4 query/key points, 8 value points, C=256 node channels, Cz=128 pair channels. */
+#define ABX_IPA_H 12
+#define ABX_IPA_C 256
+#define ABX_IPA_CZ 128
+#define ABX_IPA_FEAT 2112   /* H*(16 + 8*3 + 8 + Cz) */
+
+/* bytes of workspace abx_ipa_forward / abx_ipa_attention_features need for a [B,N] problem (upper bound:
+ * includes room for the pair-bias tensor used when pair_bias == NULL) */
+size_t abx_ipa_workspace_bytes(int B, int N);
+
+/* pair_bias[b,h,i,j] = sqrt(1/3) * (z[b,i,j,:] . w_pair[h,:] + b_pair[h]) — folding.py:101-104.
+ * Depends only on z and the weights, so IpaScore (score_network.py:126-163, 8 weight-shared
+ * iterations over the same pair activations) evaluates it once per call. */
+int abx_ipa_pair_bias(void* stream, int B, int N, const float* z, const float* w_pair, const float* b_pair,
+                      float* pair_bias /* [B,H,N,N] */);
+
+/* InvariantPointAttention.forward (folding.py:47-132).
+ *   x [B,N,C]; z [B,N,N,Cz]; mask [B,N] f32; rots [B,N,3,3]; trans [B,N,3] (already / position_scale)
+ *   pair_bias: [B,H,N,N] from abx_ipa_pair_bias, or NULL (then computed into the workspace)
+ *   residual: optional [B,N,C] added to the output (score_network.py:128: seq_act += attn)
+ *   out [B,N,C] */
+int abx_ipa_forward(void* stream, int B, int N, const float* x, const float* z, const float* mask,
+                    const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
+                    const float* residual, float* out, void* workspace, size_t workspace_bytes);
+
+/* Stages of abx_ipa_forward, exported so tests and the benchmark can time/verify them separately. */
+/* feats [B,N,2112] = concat(o_scalar 192, o_point_local (r n) 288, o_point_norm 96, o_pair 1536) */
+int abx_ipa_attention_features(void* stream, int B, int N, const float* x, const float* z, const float* mask,
+                               const float* rots, const float* trans, const abx_ipa_weights* w,
+                               const float* pair_bias, float* feats, void* workspace, size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABX_B200_H_ */

@@ -1,0 +1,99 @@
+"""GPU parity of the IPA kernels (through the C-ABI, via the reference-shaped `InvariantPointAttention`)
+against the reference's golden output and the CPU oracle."""
+import pytest
+import torch
+
+from abx_b200.utils.weights import np_randn
+from oracle import model as M
+from oracle import quat as Q
+from tests.util import golden, maxabs, seeded_params
+
+pytestmark = pytest.mark.gpu
+
+PREFIX = M.SN + 'attention_module.'
+
+
+def make_ipa():
+    from abx_b200.model.folding import InvariantPointAttention
+    ipa = InvariantPointAttention(M.IPA_CONF, 128)
+    P = seeded_params()
+    ipa.load_state_dict({k[len(PREFIX):]: v for k, v in P.items() if k.startswith(PREFIX)}, strict=True)
+    return ipa.cuda().eval(), P
+
+
+def test_linear_matches_torch(cuda_device):
+    import ctypes
+    from abx_b200 import lib
+    L = lib.load()
+    for (m, n, k) in ((37, 6, 256), (700, 1152, 256), (129, 256, 2112), (64, 65, 20)):
+        x, w, b, r = np_randn(1, m, k), np_randn(2, n, k), np_randn(3, n), np_randn(4, m, n)
+        for relu in (0, 1):
+            y = torch.empty(m, n, device='cuda')
+            xc, wc, bc, rc = x.cuda(), w.cuda(), b.cuda(), r.cuda()
+            lib.check(L.abx_linear_f32(lib.stream(), m, n, k, lib.ptr(xc), k, lib.ptr(wc), lib.ptr(bc), lib.ptr(rc), relu,
+                                       lib.ptr(y), n))
+            ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+            ref = (ref.clamp(min=0) if relu else ref) + r.double()
+            assert maxabs(y.cpu(), ref) < 1e-5 * float(ref.abs().max()) * (k ** 0.5)
+
+
+def test_ipa_matches_reference_golden(cuda_device):
+    g = golden('ipa')
+    ipa, _ = make_ipa()
+    x, z = np_randn(211, 2, 37, 256), np_randn(212, 2, 37, 37, 128)
+    with torch.no_grad():
+        out = ipa(x.cuda(), z.cuda(), g['mask'].cuda(), (g['rots'].cuda(), g['trans'].cuda()))
+    assert maxabs(out.cpu(), g['out']) < 2e-5 * float(g['out'].abs().max())
+
+
+@pytest.mark.parametrize('B,N', [(1, 1), (1, 33), (3, 100), (2, 350)])
+def test_ipa_matches_oracle(cuda_device, B, N):
+    """Ragged masks, sizes off the tile grid, and the north-star size; features and output."""
+    ipa, P = make_ipa()
+    gen = torch.Generator().manual_seed(100 + N)
+    x, z = np_randn(300 + N, B, N, 256), np_randn(400 + N, B, N, N, 128)
+    q = torch.randn(B, N, 4, generator=gen); q = q / q.norm(dim=-1, keepdim=True)
+    rots, trans = Q.quat_to_rot(q), torch.randn(B, N, 3, generator=gen) * 2.0
+    mask = torch.ones(B, N)
+    if N > 8:
+        mask[-1, -(N // 5):] = 0                   # padded tail on the last batch element
+        mask[0, 3] = 0                             # a hole
+    ref, parts = M.ipa_forward(P, x, z, mask, rots, trans, return_parts=True)
+    with torch.no_grad():
+        args = (x.cuda(), z.cuda(), mask.cuda(), (rots.cuda(), trans.cuda()))
+        feats = ipa.attention_features(*args)
+        out = ipa(*args)
+        bias = ipa.pair_bias(z.cuda())
+        out_b = ipa(*args, pair_bias=bias, residual=x.cuda())
+    assert maxabs(feats.cpu(), parts['feats']) < 3e-5 * float(parts['feats'].abs().max())
+    assert maxabs(out.cpu(), ref) < 3e-5 * float(ref.abs().max())
+    assert maxabs(out_b.cpu(), ref + x) < 3e-5 * float((ref + x).abs().max())
+    ref_bias = (3 ** -0.5) * M.linear(P, PREFIX + 'proj_pair', z).permute(0, 3, 1, 2)
+    assert maxabs(bias.cpu(), ref_bias) < 1e-5 * float(ref_bias.abs().max())
+
+
+def test_ipa_is_frame_invariant(cuda_device):
+    """Size-independent property at full size: a global rigid motion of all frames leaves the output unchanged."""
+    ipa, _ = make_ipa()
+    B, N = 2, 350
+    gen = torch.Generator().manual_seed(77)
+    x, z = np_randn(501, B, N, 256).cuda(), np_randn(502, B, N, N, 128).cuda()
+    q = torch.randn(B, N, 4, generator=gen); q = q / q.norm(dim=-1, keepdim=True)
+    rots, trans = Q.quat_to_rot(q), torch.randn(B, N, 3, generator=gen) * 2.0
+    g = torch.randn(4, generator=gen); g = g / g.norm()
+    G, s = Q.quat_to_rot(g), torch.randn(3, generator=gen)
+    rots2 = torch.einsum('rd,bndm->bnrm', G, rots)
+    trans2 = torch.einsum('rd,bnd->bnr', G, trans) + s
+    mask = torch.ones(B, N).cuda()
+    with torch.no_grad():
+        a = ipa(x, z, mask, (rots.cuda(), trans.cuda()))
+        b = ipa(x, z, mask, (rots2.cuda(), trans2.cuda()))
+    assert maxabs(a.cpu(), b.cpu()) < 1e-4 * float(a.abs().max())
+
+
+def test_ipa_rejects_bad_arguments(cuda_device):
+    from abx_b200.lib import AbxError
+    ipa, _ = make_ipa()
+    x, z = torch.zeros(1, 4, 256), torch.zeros(1, 4, 4, 128)
+    with pytest.raises(AbxError):
+        ipa(x, z, torch.ones(1, 4), (torch.eye(3).expand(1, 4, 3, 3), torch.zeros(1, 4, 3)))     # CPU tensors

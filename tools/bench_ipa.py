@@ -1,0 +1,63 @@
+"""Micro-benchmark of one IPA layer-call (abx_ipa_forward) on cuda:0: CUDA-event time per call and the
+achieved fraction of the measured HBM peak for SURVEY §8d's algorithmic bytes.
+
+    python tools/bench_ipa.py [--B 8] [--N 350] [--iters 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--B', type=int, default=8)
+    ap.add_argument('--N', type=int, default=350)
+    ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--precomputed-bias', type=int, default=1)
+    a = ap.parse_args()
+    from abx_b200.model.folding import InvariantPointAttention
+    from abx_b200.utils.weights import load_seeded_
+    conf = dict(num_head=12, num_channel=256, num_scalar_qk=16, num_scalar_v=16, num_point_qk=4, num_point_v=8)
+    ipa = load_seeded_(InvariantPointAttention(conf, 128), 0).cuda().eval()
+    B, N = a.B, a.N
+    g = torch.Generator(device='cuda').manual_seed(0)
+    x = torch.randn(B, N, 256, device='cuda', generator=g)
+    z = torch.randn(B, N, N, 128, device='cuda', generator=g)
+    q = torch.randn(B, N, 4, device='cuda', generator=g); q = q / q.norm(dim=-1, keepdim=True)
+    from abx_b200.model.quat_affine import quat_to_rot
+    rots, trans = quat_to_rot(q), torch.randn(B, N, 3, device='cuda', generator=g) * 2
+    mask = torch.ones(B, N, device='cuda')
+    bias = ipa.pair_bias(z) if a.precomputed_bias else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    with torch.no_grad():
+        for _ in range(3):
+            ipa(x, z, mask, (rots, trans), pair_bias=bias)
+        times = []
+        for _ in range(a.iters):
+            flush.zero_()                                     # evict z from the 126 MB L2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ipa(x, z, mask, (rots, trans), pair_bias=bias)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+    times.sort()
+    ms = times[len(times) // 2]
+    alg = B * 4 * (128 * N * N + 2 * 256 * N + 12 * N + N) + 4 * 838552
+    peak = 6550.7
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))['hbm_gbs']
+    except Exception:
+        pass
+    gbs = alg / (ms * 1e-3) / 1e9
+    print(json.dumps(dict(B=B, N=N, ms_per_layer_call=ms, us_per_element=ms * 1e3 / B, algorithmic_bytes=alg,
+                          achieved_gbs=gbs, peak_gbs=peak, frac=gbs / peak, precomputed_bias=bool(a.precomputed_bias))))
+
+
+if __name__ == '__main__':
+    main()
