@@ -393,16 +393,14 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   }
 
   const size_t asmem = attn_smem_bytes(N);
-  if (asmem > 48 * 1024)
-    ABX_CUDA(cudaFuncSetAttribute(ipa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+  ABX_CUDA(cudaFuncSetAttribute(ipa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
   ipa_attention_kernel<<<dim3(ceil_div(N, kRows), kH, B), kAttnThreads, asmem, s>>>(
       N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, feats);
   count_launch();
   if ((rc = check_launch("ipa_attention_kernel"))) return rc;
 
   const size_t gsmem = agg_smem_bytes(N);
-  if (gsmem > 48 * 1024)
-    ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+  ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
   ipa_pair_aggregate_kernel<<<dim3(N, B), kAggThreads, gsmem, s>>>(N, z, ws.probs, feats);
   count_launch();
   return check_launch("ipa_pair_aggregate_kernel");

@@ -101,7 +101,7 @@ class FullDiffuser:
         if trans_t is not None:
             args[2], args[3] = trans_t.float().contiguous(), trans_0.float().contiguous()
             trans = torch.empty(B, N, 3, device=dev, dtype=torch.float32 if is32 else torch.float64)
-        with torch.cuda.device(dev):
+        with lib.device_guard(ref):
             lib.check(self._lib.abx_se3_scores(lib.stream(), B, N, ctypes.byref(self._consts),
                                                *(lib.ptr(a) for a in args), lib.ptr(t64), is32, lib.ptr(tab),
                                                lib.ptr(sig), lib.ptr(om), lib.ptr(rot), lib.ptr(trans)))
@@ -141,7 +141,7 @@ class FullDiffuser:
         B, N = seq_t.shape
         t64, _ = self._t64(t)
         out = torch.empty(B, N, 20, device=logits_t.device, dtype=torch.float32)
-        with torch.cuda.device(logits_t.device):
+        with lib.device_guard(logits_t):
             lib.check(self._lib.abx_seq_reverse_rates(lib.stream(), B, N, ctypes.byref(self._consts),
                                                       lib.ptr(seq_t.long().contiguous()),
                                                       lib.ptr(logits_t.float().contiguous()), lib.ptr(t64),
@@ -174,7 +174,7 @@ class FullDiffuser:
         mask = None if diffuse_mask is None else diffuse_mask.to(torch.int32).contiguous()
         rigids = torch.empty(B, N, 7, device=dev, dtype=torch.float64)
         seq_out = torch.empty(B, N, device=dev, dtype=torch.int64)
-        with torch.cuda.device(dev):
+        with lib.device_guard(rigid_t):
             lib.check(self._lib.abx_se3_reverse_step(
                 lib.stream(), B, N, ctypes.byref(self._consts), lib.ptr(rigid_t), int(rigid_t.dtype == torch.float64),
                 lib.ptr(seq_in), lib.ptr(rot_score), lib.ptr(trans_score), lib.ptr(mask), lib.ptr(t64), dt32, sqrt_dt32,

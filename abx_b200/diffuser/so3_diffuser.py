@@ -146,7 +146,7 @@ class SO3Diffuser:
         t64 = t.to(torch.float64).contiguous()
         is32 = int(t.dtype != torch.float64)
         L = lib.load()
-        with torch.cuda.device(v.device):
+        with lib.device_guard(v):
             if self.use_cached_score:
                 lib.check(L.abx_so3_score_rotvec(lib.stream(), B, N, ctypes.byref(self._consts), lib.ptr(v),
                                                  lib.ptr(t64), is32, lib.ptr(tab), lib.ptr(sig), lib.ptr(om), lib.ptr(out)))

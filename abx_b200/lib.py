@@ -87,6 +87,13 @@ def ptr(t, dtype=None):
     return t.data_ptr()
 
 
+def device_guard(t):
+    """Context manager selecting the tensor's CUDA device; CPU tensors are refused (no fallback)."""
+    if not t.is_cuda:
+        raise AbxError('abx_b200 kernels take CUDA tensors only (no CPU fallback)')
+    return torch.cuda.device(t.device)
+
+
 def stream():
     return torch.cuda.current_stream().cuda_stream
 

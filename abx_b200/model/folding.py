@@ -69,7 +69,7 @@ class InvariantPointAttention(nn.Module):
         B, N = inputs_2d.shape[:2]
         z = inputs_2d.float().contiguous()
         out = torch.empty(B, self.config.num_head, N, N, device=z.device, dtype=torch.float32)
-        with torch.cuda.device(z.device):
+        with lib.device_guard(z):
             lib.check(self._lib.abx_ipa_pair_bias(lib.stream(), B, N, lib.ptr(z), lib.ptr(self.proj_pair.weight.detach()),
                                                   lib.ptr(self.proj_pair.bias.detach()), lib.ptr(out)))
         return out
@@ -88,7 +88,7 @@ class InvariantPointAttention(nn.Module):
         out = torch.empty(B, N, self.config.num_channel, device=dev, dtype=torch.float32)
         nbytes = self._lib.abx_ipa_workspace_bytes(B, N)
         ws = WORKSPACE.get(nbytes, dev)
-        with torch.cuda.device(dev):
+        with lib.device_guard(inputs_1d):
             lib.check(self._lib.abx_ipa_forward(
                 lib.stream(), B, N, lib.ptr(x), lib.ptr(z), lib.ptr(m), lib.ptr(rots), lib.ptr(trans),
                 ctypes.byref(self._weights()), lib.ptr(pair_bias), lib.ptr(residual), lib.ptr(out), lib.ptr(ws), nbytes))
@@ -102,7 +102,7 @@ class InvariantPointAttention(nn.Module):
         feats = torch.empty(B, N, 2112, device=dev, dtype=torch.float32)
         nbytes = self._lib.abx_ipa_workspace_bytes(B, N)
         ws = WORKSPACE.get(nbytes, dev)
-        with torch.cuda.device(dev):
+        with lib.device_guard(inputs_1d):
             lib.check(self._lib.abx_ipa_attention_features(
                 lib.stream(), B, N, lib.ptr(inputs_1d.float().contiguous()), lib.ptr(inputs_2d.float().contiguous()),
                 lib.ptr(mask.to(torch.float32).contiguous()), lib.ptr(rots.float().contiguous()),
