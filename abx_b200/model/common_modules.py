@@ -8,12 +8,15 @@ from torch.nn import LayerNorm  # noqa: F401  (re-exported, as the reference doe
 class ConfigView(dict):
     """Attribute access over a (nested) dict; accepts ml_collections.ConfigDict-like objects too."""
 
+    def __getitem__(self, k):
+        v = dict.__getitem__(self, k)
+        return ConfigView(v) if isinstance(v, dict) and not isinstance(v, ConfigView) else v
+
     def __getattr__(self, k):
         try:
-            v = self[k]
+            return self[k]
         except KeyError as e:
             raise AttributeError(k) from e
-        return ConfigView(v) if isinstance(v, dict) else v
 
     def get(self, k, default=None):
         v = dict.get(self, k, default)

@@ -1,0 +1,284 @@
+"""Trunk of the score network: input embeddings + one Seqformer block (reference: abx/model/seqformer.py).
+
+Same module tree / parameter names as the reference (checkpoints load with strict=True).  This round the
+block runs as PyTorch ops on the GPU (SURVEY §8f-1 lists its kernels as the next widening step); what is
+restructured here is (a) the step-invariant part of the embeddings is computed once per complex
+(`static_embeddings`) and (b) attention goes through fused scaled-dot-product attention so the
+[B,N,4,N,N] triangle-attention logits are not materialised when a fused backend is available.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from abx_b200.model.common_modules import LayerNorm, Linear, as_config
+from abx_b200.model.encoder import PairEmbedding, ResidueEmbedding
+
+RESTYPE_NUM, NUM_AB_REGIONS = 20, 14
+
+
+def get_timestep_embedding(timesteps, embedding_dim, max_positions=10000):
+    """seqformer.py:49-66."""
+    assert timesteps.dim() == 1 and embedding_dim % 2 == 0
+    timesteps = timesteps * max_positions
+    half = embedding_dim // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float32, device=timesteps.device) * -(math.log(max_positions) / (half - 1)))
+    arg = timesteps.float()[:, None] * freq[None, :]
+    return torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
+
+
+class Attention(nn.Module):
+    """seqformer.py:228-301 (gating on, no inception kernels)."""
+
+    def __init__(self, input_dim, key_dim, value_dim, gating=True, num_head=4, split_first=True):
+        super().__init__()
+        assert key_dim % num_head == 0 and value_dim % num_head == 0 and gating
+        self.key_dim, self.value_dim, self.num_head, self.split_first = key_dim, value_dim, num_head, split_first
+        if split_first:
+            self.proj_q = Linear(input_dim, key_dim, init='attn', bias=False)
+            self.proj_k = Linear(input_dim, key_dim, init='attn', bias=False)
+            self.proj_v = Linear(input_dim, value_dim, init='attn', bias=False)
+        else:
+            assert key_dim == value_dim
+            self.proj_in = Linear(input_dim, key_dim * 3, init='attn', bias=False)
+        self.gate = Linear(input_dim, value_dim, init='gate')
+        self.proj_out = Linear(value_dim, input_dim, init='final')
+
+    def forward(self, q_data, k_data=None, bias=None, k_mask=None):
+        """q_data [B,S,L,C]; bias [B,H,L,L] (shared over S); k_mask [B,S|1,L] bool."""
+        H = self.num_head
+        if self.split_first:
+            q, k, v = self.proj_q(q_data), self.proj_k(k_data), self.proj_v(k_data)
+            q, k, v = (x.reshape(x.shape[:-1] + (H, -1)).transpose(-2, -3) for x in (q, k, v))        # b s h l d
+        else:
+            t = self.proj_in(q_data)
+            t = t.reshape(t.shape[:-1] + (H, -1)).transpose(-2, -3)
+            q, k, v = torch.chunk(t, 3, dim=-1)
+        add = bias[:, None]                                                                           # b 1 h q k
+        neg = torch.finfo(q.dtype).min
+        add = add.masked_fill(~k_mask[:, :, None, None, :].bool(), neg) if k_mask is not None else add
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=add.expand(q.shape[:-1] + (k.shape[-2],)))
+        o = o.transpose(-2, -3).reshape(q_data.shape[:-1] + (-1,))
+        return self.proj_out(o * torch.sigmoid(self.gate(q_data)))
+
+
+class SeqAttentionWithPairBias(nn.Module):
+    def __init__(self, config, num_in_seq_channel, num_in_pair_channel):
+        super().__init__()
+        self.seq_norm = LayerNorm(num_in_seq_channel)
+        self.pair_norm = LayerNorm(num_in_pair_channel)
+        self.proj_pair = Linear(num_in_pair_channel, config.num_head, init='linear', bias=False)
+        self.attn = Attention(num_in_seq_channel, num_in_seq_channel, num_in_seq_channel, num_head=config.num_head,
+                              split_first=False)
+        self.config = config
+
+    def forward(self, seq_act, pair_act, mask):
+        s = self.seq_norm(seq_act)
+        bias = self.proj_pair(self.pair_norm(pair_act)).permute(0, 3, 1, 2)
+        return self.attn(s[:, None], bias=bias, k_mask=mask[:, None, :])[:, 0]
+
+
+class Transition(nn.Module):
+    def __init__(self, config, num_in_channel):
+        super().__init__()
+        inter = num_in_channel * config.num_intermediate_factor
+        self.transition = nn.Sequential(LayerNorm(num_in_channel), Linear(num_in_channel, inter, init='linear'), nn.ReLU(),
+                                        Linear(inter, num_in_channel, init='final'))
+
+    def forward(self, act, mask=None):
+        return self.transition(act)
+
+
+class OuterProductMean(nn.Module):
+    def __init__(self, config, num_in_channel, num_out_channel):
+        super().__init__()
+        c = config
+        self.norm = LayerNorm(num_in_channel)
+        self.left_proj = Linear(num_in_channel, c.num_outer_channel, init='linear')
+        self.right_proj = Linear(num_in_channel, c.num_outer_channel, init='linear')
+        self.out_proj = Linear(2 * c.num_outer_channel, num_out_channel, init='final')
+
+    def forward(self, act, mask):
+        """seqformer.py:378-411: concat(left_j * right_i, left_j - right_i) -> out_proj."""
+        m = mask[:, :, None].to(act.dtype)
+        a = self.norm(act)
+        left, right = m * self.left_proj(a), m * self.right_proj(a)
+        prod = left[:, None, :, :] * right[:, :, None, :]
+        diff = left[:, None, :, :] - right[:, :, None, :]
+        return self.out_proj(torch.cat([prod, diff], dim=-1))
+
+
+class TriangleMultiplication(nn.Module):
+    def __init__(self, config, num_in_channel):
+        super().__init__()
+        c = config
+        inter = c.num_intermediate_channel
+        self.norm = LayerNorm(num_in_channel)
+        self.left_proj = Linear(num_in_channel, inter, init='linear')
+        self.right_proj = Linear(num_in_channel, inter, init='linear')
+        self.final_norm = LayerNorm(inter)
+        self.left_gate = Linear(num_in_channel, inter, init='gate')
+        self.right_gate = Linear(num_in_channel, inter, init='gate')
+        self.final_gate = Linear(num_in_channel, num_in_channel, init='gate')
+        self.proj_out = Linear(inter, num_in_channel, init='final')
+        self.outgoing = c.orientation == 'per_row'
+        self.config = c
+
+    def forward(self, act, mask):
+        """seqformer.py:413-504."""
+        pm = (mask[:, :, None] * mask[:, None, :])[..., None].to(act.dtype)
+        act = self.norm(act)
+        left = pm * self.left_proj(act) * torch.sigmoid(self.left_gate(act))
+        right = pm * self.right_proj(act) * torch.sigmoid(self.right_gate(act))
+        # channel-major so the triangle product is one batched GEMM per channel
+        lt, rt_ = left.permute(0, 3, 1, 2), right.permute(0, 3, 1, 2)                 # b c i k
+        if self.outgoing:
+            out = torch.matmul(lt, rt_.transpose(-1, -2))                            # sum_k l[i,k] r[j,k]
+        else:
+            out = torch.matmul(lt.transpose(-1, -2), rt_)                            # sum_k l[k,i] r[k,j]
+        out = self.proj_out(self.final_norm(out.permute(0, 2, 3, 1)))
+        return out * torch.sigmoid(self.final_gate(act))
+
+
+class TriangleAttention(nn.Module):
+    def __init__(self, config, num_in_pair_channel):
+        super().__init__()
+        c = config
+        self.norm = LayerNorm(num_in_pair_channel)
+        self.proj_pair = Linear(num_in_pair_channel, c.num_head, init='linear', bias=False)
+        self.attn = Attention(num_in_pair_channel, num_in_pair_channel, num_in_pair_channel, gating=c.gating,
+                              num_head=c.num_head, split_first=True)
+        self.per_column = c.orientation == 'per_column'
+        self.config = c
+
+    def forward(self, pair_act, seq_mask):
+        """seqformer.py:506-550."""
+        if self.per_column:
+            pair_act = pair_act.transpose(1, 2)
+        pair_act = self.norm(pair_act)
+        bias = self.proj_pair(pair_act).permute(0, 3, 1, 2)
+        out = self.attn(pair_act, pair_act, bias=bias, k_mask=seq_mask[:, None, :])
+        return out.transpose(1, 2) if self.per_column else out
+
+
+class SeqformerIteration(nn.Module):
+    def __init__(self, config, seq_channel, pair_channel):
+        super().__init__()
+        c = config
+        self.seq_attn = SeqAttentionWithPairBias(c.seq_attention_with_pair_bias, seq_channel, pair_channel)
+        self.seq_transition = Transition(c.seq_transition, seq_channel)
+        self.outer_product_mean = OuterProductMean(c.outer_product_mean, seq_channel, pair_channel)
+        self.triangle_multiplication_outgoing = TriangleMultiplication(c.triangle_multiplication_outgoing, pair_channel)
+        self.triangle_multiplication_incoming = TriangleMultiplication(c.triangle_multiplication_incoming, pair_channel)
+        self.triangle_attention_starting_node = TriangleAttention(c.triangle_attention_starting_node, pair_channel)
+        self.triangle_attention_ending_node = TriangleAttention(c.triangle_attention_ending_node, pair_channel)
+        self.pair_transition = Transition(c.pair_transition, pair_channel)
+        self.config = config
+
+    def forward(self, seq_act, pair_act, seq_mask):
+        """seqformer.py:569-606 (inference: dropout is the identity)."""
+        seq_act = seq_act + self.seq_attn(seq_act, pair_act, seq_mask)
+        seq_act = seq_act + self.seq_transition(seq_act)
+        pair_act = pair_act + self.outer_product_mean(seq_act, seq_mask)
+        mf = seq_mask.to(pair_act.dtype)
+        pair_act = pair_act + self.triangle_multiplication_outgoing(pair_act, mf)
+        pair_act = pair_act + self.triangle_multiplication_incoming(pair_act, mf)
+        pair_act = pair_act + self.triangle_attention_starting_node(pair_act, seq_mask)
+        pair_act = pair_act + self.triangle_attention_ending_node(pair_act, seq_mask)
+        pair_act = pair_act + self.pair_transition(pair_act)
+        return seq_act, pair_act
+
+
+class Seqformer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        c = config
+        self.blocks = nn.ModuleList([
+            SeqformerIteration(c.seqformer, c.seq_channel + c.index_embed_size, c.pair_channel + 2 * c.index_embed_size)
+            for _ in range(c.seqformer_num_block)])
+
+    def forward(self, seq_act, pair_act, mask, is_recycling=True):
+        for block in self.blocks:
+            seq_act, pair_act = block(seq_act, pair_act, mask)
+        return seq_act, pair_act
+
+
+class EmbeddingAndSeqformer(nn.Module):
+
+    def __init__(self, config):
+        super().__init__()
+        c = as_config(config)
+        if c.esm.enabled:
+            raise NotImplementedError('ESM2 conditioning needs the fair-esm package and esm2_t36_3B weights, which are '
+                                      'not available offline; set embeddings_and_seqformer.esm.enabled=false')
+        self.num_token = RESTYPE_NUM + 3
+        self.num_region = NUM_AB_REGIONS + 1
+        self.proj_aa_type = nn.Embedding(self.num_token, c.seq_channel, padding_idx=20)
+        self.encode_residue_emb = ResidueEmbedding(c)
+        self.encode_pair_emb = PairEmbedding(c)
+        self.aa_proj = nn.Sequential(LayerNorm(c.seq_channel), Linear(c.seq_channel, c.seq_channel), nn.ReLU(),
+                                     Linear(c.seq_channel, c.seq_channel))
+        self.proj_rel_pos = nn.Embedding(c.max_relative_feature * 2 + 2, c.pair_channel)
+        if c.recycle_features:
+            self.prev_seq_norm = LayerNorm(c.seq_channel + c.index_embed_size)
+            self.prev_pair_norm = LayerNorm(c.pair_channel + 2 * c.index_embed_size)
+        if c.recycle_pos:
+            self.proj_prev_pos = nn.Embedding(c.prev_pos.num_bins, c.pair_channel + 2 * c.index_embed_size)
+        self.seqformer = Seqformer(c)
+        self.config = c
+        self._static = None          # (seq_static, pair_static) of the current complex, see static_embeddings
+
+    # ---- step-invariant part of the embeddings ---------------------------------------------------------
+    def static_embeddings(self, batch):
+        """Everything in seqformer.py:176-207 that does not depend on the diffused residues or on t:
+        antigen sequence embedding, relative-position pair embedding, ResidueEmbedding and PairEmbedding
+        (both see fixed residues only).  Returns (seq_static [B,N,C] with zeros in the antibody sequence
+        embedding slot, pair_static [B,N,N,Cz])."""
+        c = self.config
+        n_ab = batch['anchor_flag'].shape[1]
+        residx = batch['residx']
+
+        def relpos(pos):
+            off = pos[:, None, :] - pos[:, :, None]
+            return torch.clip(off + c.max_relative_feature, min=0, max=2 * c.max_relative_feature) + 1
+
+        ag_seq = self.aa_proj(self.proj_aa_type(batch['seq'][:, n_ab:]))
+        B, N = batch['seq'].shape
+        seq_static = self.encode_residue_emb(batch).clone()
+        seq_static[:, n_ab:] += ag_seq
+        pair_static = self.encode_pair_emb(batch).clone()
+        pair_static[:, :n_ab, :n_ab] += self.proj_rel_pos(relpos(residx[:, :n_ab]))                   # pair_concat :24-45
+        pair_static[:, n_ab:, n_ab:] += self.proj_rel_pos(relpos(residx[:, n_ab:]))
+        return seq_static, pair_static
+
+    def cache_static(self, batch):
+        """Evaluate the static embeddings once for a complex (first batch element; all samples of a batch
+        share the complex) and reuse them in every later forward until `clear_static()`."""
+        one = {k: (v[:1] if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in batch.items()}
+        self._static = self.static_embeddings(one)
+
+    def clear_static(self):
+        self._static = None
+
+    def forward(self, batch):
+        c = self.config
+        seq_t = batch['seq_t']
+        n_ab = batch['anchor_flag'].shape[1]
+        B, N = seq_t.shape
+        seq_static, pair_static = self._static if self._static is not None else self.static_embeddings(batch)
+
+        te = get_timestep_embedding(batch['t'], c.index_embed_size)                                   # Embedder :93-119
+        ab_seq = self.proj_aa_type(seq_t[:, :n_ab].long())
+        seq_act = torch.cat([F.pad(ab_seq, (0, 0, 0, N - n_ab)) + seq_static, te[:, None, :].expand(B, N, -1)], dim=-1).float()
+        pair_act = torch.cat([pair_static.expand(B, -1, -1, -1), te[:, None, None, :].expand(B, N, N, -1),
+                              te[:, None, None, :].expand(B, N, N, -1)], dim=-1).float()
+        # _cross_concat: channel block 1 = t-embedding of residue i, block 2 = of residue j (both equal te[b])
+        if c.recycle_features:
+            if 'prev_seq' in batch:
+                seq_act = seq_act + self.prev_seq_norm(batch['prev_seq'])
+            if 'prev_pair' in batch:
+                pair_act = pair_act + self.prev_pair_norm(batch['prev_pair'])
+        if c.recycle_pos and 'prev_pos' in batch:
+            pair_act = pair_act + self.proj_prev_pos(batch['prev_pos'])
+        return self.seqformer(seq_act, pair_act, mask=batch['mask'], is_recycling=batch.get('is_recycling', True))
