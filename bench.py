@@ -1,0 +1,359 @@
+"""Benchmark of the AbX reverse-diffusion sampling hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Metric (BASELINE.json): designed-CDR samples/sec, 100-step reverse diffusion, synthetic N=350
+antibody-antigen complex (heavy 120 + light 110 + antigen 120), H3 design, random-init (seeded) weights,
+ESM disabled.  One "step" = one batched run of the whole sampler (`--samples-per-step` independent samples
+per GPU: t=1 prior draw, self-conditioning warm-up, 99 model+reverse steps, final x0 call = 101
+ScoreNetwork forwards = 2424 IPA layer-calls).  Under torchrun every rank runs its own samples of the same
+complex (weak scaling, no data-path collective; inputs are broadcast from rank 0 once and the designed
+coordinates are gathered to rank 0 every step).
+
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU oracle (the restatement of the
+reference's PyTorch code, oracle/) on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'designed_cdr_samples_per_sec'
+UNIT = 'samples/s'
+NUM_T = 100
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--samples-per-step', type=int, default=4, help='independent samples batched per GPU per step')
+    ap.add_argument('--n-antigen', type=int, default=120, help='antigen residues (N = 230 + this)')
+    ap.add_argument('--num-t', type=int, default=NUM_T)
+    ap.add_argument('--cpu-steps', type=int, default=1, help='reverse iterations timed for the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload_config(a, n_res):
+    return {'workload': f'synthetic H120+L110+A{a.n_antigen} complex (N={n_res}), generate_area=H3, T={a.num_t}, '
+                        f'num_recycle=2, ESM disabled, seeded random weights',
+            'n_res': n_res, 'num_t': a.num_t, 'samples_per_gpu_per_step': a.samples_per_step,
+            'model_forwards_per_sample': a.num_t + 1, 'ipa_layer_calls_per_sample': 24 * (a.num_t + 1),
+            'parallelism': f'dp{a.gpus} (independent samples per rank, no data-path collective)',
+            'l2': 'pair activations of one batched IPA call (samples_per_step x 62.7 MB) exceed the 126 MB L2'}
+
+
+def model_config():
+    cfg = json.load(open(os.path.join(ROOT, 'abx_b200', 'config', 'config_model.json')))
+    cfg['model']['embeddings_and_seqformer']['esm']['enabled'] = False
+    cfg['diffuser']['so3']['use_cached_score'] = True                       # inference.py:99
+    cfg['diffuser']['so3']['cache_dir'] = os.environ.get('ABX_IGSO3_CACHE', '/tmp/abx_b200_cache/')
+    return cfg
+
+
+def feature_config(cfg, device, diffuser=None):
+    feats = json.load(open(os.path.join(ROOT, 'abx_b200', 'config', 'config_data_feature.json')))
+    for name, kw in feats:
+        if 'device' in kw:
+            kw['device'] = device
+        if name == 'make_diffuser_features':
+            kw['diff_conf'] = cfg['diffuser']
+            kw.pop('optimize_steps', None)
+            kw['diffuser'] = diffuser
+    return feats
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(a, cfg, score_norms=None, threads=None):
+    """samples/s of the CPU oracle (oracle/: restatement of the reference's PyTorch-CPU path, float32) on this
+    host: `cpu_steps` iterations of the reverse loop (ScoreNetwork forward = 3 trunk passes + get_prev + reverse
+    step) at the same N, batch 1 (the reference's operating point), after the self-conditioning warm-up call;
+    per-step cost does not depend on t, so samples/s = 1 / ((T+1) t_model + (T-1) t_reverse)."""
+    import json as _json
+    import numpy as np
+    import torch
+    from abx_b200.data.synthetic import synthetic_complex
+    from abx_b200.model import features as F_
+    from abx_b200.utils.weights import seeded_state_dict
+    from oracle import diffusers as OD
+    from oracle import sampler as OS
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    shapes = {k: tuple(v) for k, v in _json.load(open(os.path.join(ROOT, 'tests', 'golden', 'state_dict_shapes.json'))).items()}
+    P = seeded_state_dict(shapes, 0)
+    batch = synthetic_complex(n_antigen=a.n_antigen, seed=0, batch_size=1)
+    for name in ('make_restype_atom_constants', 'make_gt_frames', 'make_torsion_angles'):
+        batch = F_._feats_fn[name](is_training=False)(batch)
+    diffused, _ = F_.design_mask(batch, 'H3')
+    from abx_b200.model import r3
+    rig0 = r3.rigids_to_tensor7((batch['rigidgroups_gt_frames'][0][:, :, 0], batch['rigidgroups_gt_frames'][1][:, :, 0]))
+    N = rig0.shape[1]
+    if score_norms is None:           # well-conditioned analytic stand-in: the table's VALUES do not affect the timing
+        score_norms = torch.zeros(1000, 1000)
+    od = OD.OracleDiffuser(score_norms, cdf=torch.linspace(0, 1, 1000)[None].repeat(1000, 1))
+    g = torch.Generator().manual_seed(0)
+    rig, seq = od.sample_ref(rig0, batch['seq'], diffused, torch.randn(1, N, 3, generator=g), torch.rand(1, N, generator=g),
+                             torch.randn(1, N, 3, generator=g), torch.randint(0, 20, (1, N), generator=g))
+    batch.update(rigids_t=rig, seq_t=seq, fixed_mask=1 - diffused, t=torch.ones(1))
+    grid = OS.reverse_grid(a.num_t)
+    dt = torch.tensor(1 / a.num_t)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        batch = OS.self_condition(P, od, batch, grid[0])
+        t_model = time.perf_counter() - t0
+        t_models, t_revs = [t_model], []
+        for k in range(a.cpu_steps):
+            noise = (torch.randn(1, N, 3, generator=g), torch.randn(1, N, 3, generator=g), lambda r: torch.poisson(r, generator=g))
+            t1 = time.perf_counter()
+            B = 1
+            t_ = torch.tile(torch.tensor(np.float64(grid[k])), (B,))
+            batch['t'] = t_ * torch.ones(B)
+            from oracle import model as OM
+            out = OM.score_network(P, od, batch)
+            batch.update(OM.get_prev(batch, out))
+            t2 = time.perf_counter()
+            rig, seq = od.reverse(batch['rigids_t'], batch['seq_t'], out['rot_score'], out['trans_score'], out['logits'], t_, dt,
+                                  OS.diffuse_mask_of(batch), *noise)
+            t3 = time.perf_counter()
+            batch['rigids_t'], batch['seq_t'] = rig, seq
+            t_models.append(t2 - t1)
+            t_revs.append(t3 - t2)
+    tm = statistics.mean(t_models)
+    tr = statistics.mean(t_revs) if t_revs else 0.0
+    rate = 1.0 / ((a.num_t + 1) * tm + (a.num_t - 1) * tr)
+    return {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': f'{len(t_models)} ScoreNetwork forwards ({tm:.2f} s each) + {len(t_revs)} reverse steps ({tr * 1e3:.1f} ms each) '
+                      f'of the T={a.num_t} loop at N={N}, batch 1, float32 torch-CPU oracle; extrapolated x({a.num_t + 1}, {a.num_t - 1})'}
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cfg = model_config()
+    vals = []
+    base = None
+    for i in range(a.warmup + a.steps):
+        base = cpu_oracle_rate(a, cfg)
+        if i >= a.warmup:
+            vals.append(base['value'])
+        if i == 0 and a.warmup + a.steps > 1 and 1.0 / base['value'] / (a.num_t + 1) > 20:
+            break                      # very slow host: one bounded sample is all a few minutes allow
+    if not vals:
+        vals = [base['value']]
+    v = statistics.mean(vals)
+    n_res = 230 + a.n_antigen
+    base['value'] = v
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': 1e3 / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload_config(a, n_res), 'cpu_baseline': base,
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from abx_b200 import lib, sampler
+    from abx_b200.data.synthetic import synthetic_complex
+    from abx_b200.diffuser.full_diffuser import FullDiffuser
+    from abx_b200.model import features as F_
+    from abx_b200.model import folding
+    from abx_b200.model.abx import ScoreNetwork
+    from abx_b200.utils.weights import load_seeded_
+
+    cfg = model_config()
+    if world > 1:                       # one rank builds the IGSO(3) cache, the others load it
+        if rank == 0:
+            fd = FullDiffuser(cfg['diffuser'])
+        dist.barrier()
+        if rank != 0:
+            fd = FullDiffuser(cfg['diffuser'])
+    else:
+        fd = FullDiffuser(cfg['diffuser'])
+    model = load_seeded_(ScoreNetwork(cfg['model'], fd), 0).to(dev).eval()
+    S = a.samples_per_step
+
+    # host-side inputs (pinned) for the end-to-end arm; rank 0's complex is broadcast so every rank designs the same one
+    raw = synthetic_complex(n_antigen=a.n_antigen, seed=0, batch_size=S)
+    dev_fields = ['seq', 'mask', 'chain_id', 'atom14_gt_positions', 'atom14_gt_exists', 'cdr_def', 'residx', 'anchor_flag']
+    host = {k: (v.pin_memory() if k in dev_fields else v) for k, v in raw.items()}
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in dev_fields)
+    n_res = host['seq'].shape[1]
+    n_ab = host['anchor_flag'].shape[1]
+    if world > 1:
+        for k in dev_fields:
+            t = host[k].to(dev)
+            dist.broadcast(t, 0)
+            host[k].copy_(t.cpu())
+    feat_cfg = feature_config(cfg, dev, fd)
+    static_cfg, diff_cfg = feat_cfg[:-1], feat_cfg[-1:]
+
+    def features_from_host():
+        b = {k: (v.to(dev, non_blocking=True) if k in dev_fields else v) for k, v in host.items()}
+        return F_.FeatureBuilder(static_cfg).build(b)
+
+    resident = features_from_host()
+    gather_buf = [torch.empty(S, n_ab, 14, 3, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    ipa_events = []
+    orig_forward = folding.InvariantPointAttention.forward
+
+    def timed_forward(self, *args, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_forward(self, *args, **kw)
+        e1.record()
+        ipa_events.append((e0, e1))
+        return out
+
+    def one_step(step, e2e):
+        gen = torch.Generator(device=dev).manual_seed(1000 + step * world + rank)
+        torch.manual_seed(1000 + step * world + rank)
+        base = features_from_host() if e2e else {k: v for k, v in resident.items()}
+        batch = F_.FeatureBuilder(diff_cfg).build(dict(base))                          # t = 1 prior draw
+        traj, _ = sampler.sample_loop(batch, cfg, fd, model, mode='design', num_t=a.num_t, generator=gen)
+        atom14 = traj[-1]['atom14_results'].contiguous()
+        if world > 1:
+            dist.gather(atom14, gather_buf, dst=0)
+        d2h = 0
+        if e2e:
+            res = (atom14.cpu(), traj[-1]['seq'].cpu(), traj[-1]['pLDDT'].cpu())
+            d2h = sum(x.numel() * x.element_size() for x in res)
+        return d2h
+
+    def timed(nsteps, e2e, first_step):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d2h = 0
+        for s in range(nsteps):
+            d2h = one_step(first_step + s, e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), d2h
+
+    timed(a.warmup, False, 0)                                                          # W untimed warm-up steps
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    lib.reset_launch_count()
+    folding.InvariantPointAttention.forward = timed_forward
+    ms_total, _ = timed(a.steps, False, a.warmup)
+    folding.InvariantPointAttention.forward = orig_forward
+    launches = torch.tensor([lib.launch_count()], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(launches)
+    clock_info = clocks.stop() if rank == 0 else None
+    torch.cuda.synchronize()
+    ipa_ms = [e0.elapsed_time(e1) for e0, e1 in ipa_events]
+    ms_e2e, d2h_bytes = timed(a.steps, True, a.warmup + a.steps)
+
+    if rank == 0:
+        total_samples = world * S * a.steps
+        value = total_samples / (ms_total * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = peaks.get('hbm_gbs', 6650.0)
+        alg = S * 4 * (128 * n_res * n_res + 2 * 256 * n_res + 12 * n_res + n_res) + 4 * 838552     # SURVEY §8d, per layer-call
+        ipa_mean = statistics.mean(ipa_ms)
+        achieved = alg / (ipa_mean * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(a, n_res),
+            'e2e': {'value': total_samples / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
+                    'd2h_bytes_per_step': d2h_bytes},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'kernel': 'IPA layer-call (abx_ipa_forward: node GEMMs + pack + attention + '
+                                                   'pair aggregation + final projection)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 (of fallback)',
+                         'algorithmic_bytes_per_launch': alg, 'ms_per_launch': ipa_mean, 'launches_timed': len(ipa_ms),
+                         'share_of_step': sum(ipa_ms) / ms_total, 'traffic': None},
+            'clocks': clock_info,
+        }
+        if not a.no_cpu_baseline:
+            try:
+                line['cpu_baseline'] = cpu_oracle_rate(a, cfg, score_norms=fd._so3_diffuser._score_norms)
+            except Exception as e:                                   # never lose the GPU numbers to a host-side problem
+                line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {e}'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
