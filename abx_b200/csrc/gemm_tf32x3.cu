@@ -1,0 +1,471 @@
+// fp32-accurate dense GEMM on the 5th-generation tensor cores:  y = act(x W^T + b) (+ residual)
+//
+// torch.nn.Linear semantics of the reference's `Linear` (abx/model/common_modules.py:11-59) for the node
+// and pair GEMMs of the score network (IPA projections folding.py:69-86,130-132; IpaScore / trunk layers).
+// The 1e-4 A parity budget of the sampler rules out single-pass TF32/bf16, so every fp32 operand is split
+// exactly into hi = x & ~0x1fff (a TF32 value) and lo = x - hi, and
+//     D = A_hi B_lo + A_lo B_hi + A_hi B_hi        (3xTF32; dropped A_lo B_lo term <= 2^-22 relative)
+// accumulates in fp32 in tensor memory.
+//
+// One CTA per 128 x BN output tile, 6 warps:
+//   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the raw fp32 A / W k-slabs
+//               (128 x 32 and BN x 32 elements) into a shared-memory ring
+//   warp 1      allocates TMEM; one elected lane issues 3 x 4 tcgen05.mma.kind::tf32 per slab and commits
+//               to the slab's `empty` barrier (and to `acc_full` after the last slab)
+//   warps 2-5   converters: split each landed slab into hi (in place) / lo (second buffer), fence the
+//               generic-proxy writes for the async proxy, arrive on `conv`; after the main loop the same
+//               warps read the accumulator with tcgen05.ld (warp w owns TMEM lanes 32 (w%4) ..) and apply
+//               the epilogue (bias, activation, residual) before storing.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace abx {
+
+namespace {
+
+constexpr int kBM = 128, kBK = 32;             // 32 fp32 = one 128-byte swizzle row
+constexpr int kThreads = 320, kConvThreads = 128, kAccThreads = 128;
+constexpr uint32_t kTileABytes = kBM * kBK * 4;
+
+template <int BN> struct GemmCfg {
+  static constexpr uint32_t kTileBBytes = BN * kBK * 4;
+  static constexpr uint32_t kStageBytes = 2 * (kTileABytes + kTileBBytes);     // raw/hi + lo for A and B
+  static constexpr int kStages = BN >= 128 ? 3 : (BN >= 64 ? 4 : 5);
+  static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;             // two partial-sum buffers
+  static constexpr uint32_t kStoreBytes = 4 * 32 * 36 * 4;                     // per-warp 32x36 transpose tiles
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStoreBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major operand tile with 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  Tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor, kind::tf32: D f32 (bits 4-5 = 1), A/B tf32 (bits 7-9 / 10-12 = 2), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Epilogue {
+  const float* bias;       // [Nout] or null
+  const float* residual;   // [M, ldy] or null (added after the activation)
+  const float* gate;       // [M, ldy] or null: y = (acc + bias) * sigmoid(gate)   (act == 2)
+  int act;                 // 0 none, 1 relu, 2 multiply by sigmoid(gate), 3 sigmoid
+};
+
+template <int ACT>
+__device__ __forceinline__ float epilogue_op(float a, float bias, float gate, float res) {
+  a += bias;
+  if (ACT == 1) a = fmaxf(a, 0.f);
+  else if (ACT == 2) a = a * (1.f / (1.f + expf(-gate)));
+  else if (ACT == 3) a = 1.f / (1.f + expf(-a));
+  return a + res;
+}
+
+// One 32 x 32 block of the output tile from the warp's smem transpose tile: lane = (row group lane/8, 4 columns
+// 4 (lane%8)), 8 passes of 4 rows; all loads are issued before the stores of a pass.
+template <int ACT>
+__device__ __forceinline__ void store_chunk(const float* st, const Epilogue& ep, float* __restrict__ y, int ldy, int row0,
+                                            int col0, int M, int Nout, int lane, bool vec_ok) {
+  const int rg = lane >> 3, col = col0 + 4 * (lane & 7);
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ep.bias) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) bv[u] = (col + u < Nout) ? __ldg(ep.bias + col + u) : 0.f;
+  }
+  const bool full4 = vec_ok && (col + 3 < Nout);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+  float4 v[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) v[p] = *reinterpret_cast<const float4*>(st + (16 * h + 4 * p + rg) * 36 + 4 * (lane & 7));
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int row = row0 + 16 * h + 4 * p + rg;
+    if (row >= M) continue;
+    const size_t o = (size_t)row * ldy + col;
+    float in[4] = {v[p].x, v[p].y, v[p].z, v[p].w}, g[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (full4) {
+      if (ACT == 2) { float4 t = *reinterpret_cast<const float4*>(ep.gate + o); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+      if (ep.residual) { float4 t = *reinterpret_cast<const float4*>(ep.residual + o); r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w; }
+      float4 out;
+      out.x = epilogue_op<ACT>(in[0], bv[0], g[0], r[0]);
+      out.y = epilogue_op<ACT>(in[1], bv[1], g[1], r[1]);
+      out.z = epilogue_op<ACT>(in[2], bv[2], g[2], r[2]);
+      out.w = epilogue_op<ACT>(in[3], bv[3], g[3], r[3]);
+      *reinterpret_cast<float4*>(y + o) = out;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (col + u < Nout) {
+          const float gg = (ACT == 2) ? ep.gate[o + u] : 0.f;
+          const float rr = ep.residual ? ep.residual[o + u] : 0.f;
+          y[o + u] = epilogue_op<ACT>(in[u], bv[u], gg, rr);
+        }
+      }
+    }
+  }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
+                   int Nout, int K, Epilogue ep, float* __restrict__ y, int ldy, int trust_trunc) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  auto stage_a = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
+  auto stage_alo = [&](int s) { return stage_a(s) + kTileABytes; };
+  auto stage_b = [&](int s) { return stage_a(s) + 2 * kTileABytes; };
+  auto stage_blo = [&](int s) { return stage_b(s) + Cfg::kTileBBytes; };
+  float* store_stage = reinterpret_cast<float*>(smem + (size_t)kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * Cfg::kStageBytes + Cfg::kStoreBytes);
+  uint64_t* full = bars;                        // TMA -> converters
+  uint64_t* conv = bars + kStages;              // converters -> MMA
+  uint64_t* empty = bars + 2 * kStages;         // MMA -> TMA
+  uint64_t* acc_ready = bars + 3 * kStages;     // [2] MMA -> accumulator warps (partial sum of one k-slab in TMEM)
+  uint64_t* acc_free = bars + 3 * kStages + 2;  // [2] accumulator warps -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + kBK - 1) / kBK;
+  const int nt = (Nout + BN - 1) / BN, mt = (M + kBM - 1) / kBM;
+  const int tiles = nt * mt;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(conv + s, kConvThreads);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_ready + b, 1);
+      mbar_init(acc_free + b, kAccThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Every role walks the same static schedule: tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs
+  // running side by side share the A rows in L2); `it` counts k-slabs across tiles and drives stages / phases.
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (tile / nt) * kBM, n0 = (tile % nt) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, kTileABytes + Cfg::kTileBBytes);
+          tma_load_2d(stage_a(s), &map_a, full + s, kb * kBK, m0);
+          tma_load_2d(stage_b(s), &map_b, full + s, kb * kBK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    // The tensor core adds into its fp32 accumulator with truncation; chaining all K/8 steps in TMEM would
+    // bias the result by ~K/8 ulp.  So each k-slab (12 MMAs) starts a fresh partial sum in one of two TMEM
+    // buffers, and the accumulator warps add the partials in registers with round-to-nearest.
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          const uint32_t buf = it & 1, use = it >> 1;
+          mbar_wait(acc_free + buf, (use & 1) ^ 1);
+          mbar_wait(conv + s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_acc = tmem_base + buf * BN;
+          const uint64_t a_hi = umma_desc_sw128(smem_u32(stage_a(s))), a_lo = umma_desc_sw128(smem_u32(stage_alo(s)));
+          const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_b(s))), b_lo = umma_desc_sw128(smem_u32(stage_blo(s)));
+          // small cross terms first, then the hi*hi terms (UMMA_K = 8 tf32 = 32 bytes: +2 in the addr>>4 field)
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            umma_tf32(tmem_acc, a_hi + 2 * k, b_lo + 2 * k, idesc, k != 0);
+            umma_tf32(tmem_acc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+          }
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) umma_tf32(tmem_acc, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+          umma_commit(empty + s);                    // slab free once these MMAs have read it
+          umma_commit(acc_ready + buf);              // partial sum complete
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------- converters: raw fp32 slab -> hi (in place) + lo ----------------
+    const int ct = threadIdx.x - 64;                 // 0..127
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(full + s, ph);
+        auto split = [&](float4* hi_p, float4* lo_p, int i) {
+          float4 v = hi_p[i], h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          if (!trust_trunc) hi_p[i] = h;
+          lo_p[i] = l;
+        };
+        float4* a = reinterpret_cast<float4*>(stage_a(s));
+        float4* alo = reinterpret_cast<float4*>(stage_alo(s));
+#pragma unroll 4
+        for (int i = ct; i < (int)(kTileABytes / 16); i += kConvThreads) split(a, alo, i);
+        float4* b = reinterpret_cast<float4*>(stage_b(s));
+        float4* blo = reinterpret_cast<float4*>(stage_blo(s));
+#pragma unroll 4
+        for (int i = ct; i < (int)(Cfg::kTileBBytes / 16); i += kConvThreads) split(b, blo, i);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(conv + s);
+      }
+    }
+  } else {
+    // ---------------- accumulator / epilogue warps (6..9): thread = one output row ----------------
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m0 = (tile / nt) * kBM, n0 = (tile % nt) * BN;
+      float acc[BN];
+#pragma unroll
+      for (int c = 0; c < BN; ++c) acc[c] = 0.f;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t buf = it & 1, use = it >> 1;
+        mbar_wait(acc_ready + buf, use & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + buf * BN + (uint32_t)c0, v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c0 + c] += __uint_as_float(v[c]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(acc_free + buf);
+      }
+      // epilogue: transpose 32x32 blocks through a per-warp smem tile (row stride 36 floats: conflict-free
+      // float4 writes by row and float4 reads by 8-lane row groups) so a warp stores 4 x 128-byte row pieces
+      float* st = store_stage + q * (32 * 36);
+      const int row0 = m0 + 32 * q;
+      const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                          (!ep.residual || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) &&
+                          (!ep.gate || (reinterpret_cast<uintptr_t>(ep.gate) & 15) == 0);
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= Nout) break;
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(st + lane * 36 + c) = make_float4(acc[c0 + c], acc[c0 + c + 1], acc[c0 + c + 2], acc[c0 + c + 3]);
+        __syncwarp();
+        switch (ep.act) {
+          case 0: store_chunk<0>(st, ep, y, ldy, row0, n0 + c0, M, Nout, lane, vec_ok); break;
+          case 1: store_chunk<1>(st, ep, y, ldy, row0, n0 + c0, M, Nout, lane, vec_ok); break;
+          case 2: store_chunk<2>(st, ep, y, ldy, row0, n0 + c0, M, Nout, lane, vec_ok); break;
+          default: store_chunk<3>(st, ep, y, ldy, row0, n0 + c0, M, Nout, lane, vec_ok); break;
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// [rows, K] fp32 row-major (row stride ld elements) -> tiles of box_rows x 32 elements, 128-byte swizzle,
+// out-of-bounds elements read as zero (handles the M / Nout / K tails)
+int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  ABX_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ABX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for a [%d,%d] ld=%d operand", (int)r, rows, K, ld);
+  return ABX_OK;
+}
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+      v = 148;
+    return v;
+  }();
+  return n;
+}
+
+// The tensor core ignores the 13 low mantissa bits of a tf32 operand (verified bit for bit on B200 by
+// tools/gemm_trunc_probe.py), so the raw fp32 tile already acts as the hi part and the converters only write
+// the lo tile.  ABX_GEMM_TRUST_TRUNC=0 restores the explicit hi write-back.
+int trust_trunc() {
+  static int v = [] { const char* e = getenv("ABX_GEMM_TRUST_TRUNC"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v;
+}
+
+template <int BN>
+int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw, const Epilogue& ep,
+              float* y, int ldy) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map(&ma, x, M, K, ldx, kBM))) return rc;
+  if ((rc = make_map(&mb, w, Nout, K, ldw, BN))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ABX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(Nout, BN) * ceil_div(M, kBM);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tf32x3_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(ma, mb, M, Nout, K, ep, y, ldy, trust_trunc());
+  count_launch();
+  return check_launch("gemm_tf32x3_kernel");
+}
+
+}  // namespace
+
+bool gemm_tf32x3_supported(int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw) {
+  return M > 0 && Nout > 0 && K >= 4 && K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 && ldx >= K && ldw >= K &&
+         (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+}
+
+// act: 0 none, 1 relu, 2 multiply by sigmoid(gate[M,ldy]), 3 sigmoid.  tile_n: 0 = choose, else 32/64/128.
+int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                       const float* bias, const float* residual, const float* gate, int act, float* y, int ldy, int tile_n) {
+  Epilogue ep{bias, residual, gate, act};
+  if (tile_n == 0) {
+    // enough CTAs to cover the 148 SMs beats wide tiles for the small-M node GEMMs
+    const int mt = ceil_div(M, kBM);
+    if (Nout <= 32 || mt * ceil_div(Nout, 64) < 120) tile_n = 32;
+    else if (Nout <= 64 || mt * ceil_div(Nout, 128) < 120) tile_n = 64;
+    else tile_n = 128;
+  }
+  switch (tile_n) {
+    case 32: return launch_bn<32>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy);
+    case 64: return launch_bn<64>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy);
+    case 128: return launch_bn<128>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy);
+  }
+  set_error("abx_gemm_tf32x3: tile_n must be 0, 32, 64 or 128 (got %d)", tile_n);
+  return ABX_ERR_INVALID;
+}
+
+}  // namespace abx
+
+extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                               const float* bias, const float* residual, const float* gate, int act, float* y, int ldy,
+                               int tile_n) {
+  ABX_REQUIRE(M > 0 && Nout > 0 && K > 0 && x && w && y, "abx_gemm_tf32x3: bad shape or null argument");
+  ABX_REQUIRE(abx::gemm_tf32x3_supported(M, Nout, K, x, ldx, w, ldw),
+              "abx_gemm_tf32x3: K, ldx, ldw must be multiples of 4 with ldx, ldw >= K, and x, w 16-byte aligned "
+              "(K=%d ldx=%d ldw=%d)", K, ldx, ldw);
+  ABX_REQUIRE(ldy >= Nout, "abx_gemm_tf32x3: ldy < Nout");
+  ABX_REQUIRE(act >= 0 && act <= 3 && (act != 2 || gate), "abx_gemm_tf32x3: bad activation / missing gate");
+  return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, residual, gate, act, y, ldy, tile_n);
+}

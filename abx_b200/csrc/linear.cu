@@ -8,6 +8,9 @@ namespace abx {
 
 constexpr int kBM = 128, kBN = 64, kBK = 16, kGemmThreads = 256;
 
+int launch_linear_simt(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w,
+                       const float* bias, const float* residual, int relu, float* y, int ldy);
+
 __global__ void __launch_bounds__(kGemmThreads) linear_f32_kernel(
     int M, int Nout, int K, const float* __restrict__ x, int ldx, const float* __restrict__ w,
     const float* __restrict__ bias, const float* __restrict__ residual, int relu, float* __restrict__ y, int ldy) {
@@ -90,8 +93,27 @@ __global__ void __launch_bounds__(kGemmThreads) linear_f32_kernel(
   }
 }
 
+bool gemm_tf32x3_supported(int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw);
+int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                       const float* bias, const float* residual, const float* gate, int act, float* y, int ldy, int tile_n);
+
+static int g_backend = 0;   // 0 auto (tensor cores when the operands qualify), 1 SIMT only, 2 tensor cores only
+
+// Dense layer dispatcher used by the IPA pipeline: 3xTF32 tcgen05 GEMM (gemm_tf32x3.cu) when the operand
+// layout allows TMA, else the SIMT kernel below.
 int launch_linear_f32(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w,
                       const float* bias, const float* residual, int relu, float* y, int ldy) {
+  if (g_backend != 1 && M >= 32 && gemm_tf32x3_supported(M, Nout, K, x, ldx, w, K))
+    return launch_gemm_tf32x3(s, M, Nout, K, x, ldx, w, K, bias, residual, nullptr, relu ? 1 : 0, y, ldy, 0);
+  if (g_backend == 2) {
+    set_error("linear: operands do not qualify for the tcgen05 path (M=%d Nout=%d K=%d ldx=%d)", M, Nout, K, ldx);
+    return ABX_ERR_INVALID;
+  }
+  return launch_linear_simt(s, M, Nout, K, x, ldx, w, bias, residual, relu, y, ldy);
+}
+
+int launch_linear_simt(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w,
+                       const float* bias, const float* residual, int relu, float* y, int ldy) {
   dim3 grid(ceil_div(Nout, kBN), ceil_div(M, kBM));
   linear_f32_kernel<<<grid, kGemmThreads, 0, s>>>(M, Nout, K, x, ldx, w, bias, residual, relu, y, ldy);
   count_launch();
@@ -106,5 +128,11 @@ extern "C" int abx_linear_f32(void* stream, int M, int Nout, int K, const float*
   ABX_REQUIRE(K % 4 == 0 && ldx % 4 == 0 && ldx >= K && ldy >= Nout,
               "abx_linear_f32: K and ldx must be multiples of 4, ldx >= K, ldy >= Nout (K=%d ldx=%d ldy=%d)", K, ldx, ldy);
   ABX_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0), "abx_linear_f32: x and w must be 16-byte aligned");
-  return abx::launch_linear_f32((cudaStream_t)stream, M, Nout, K, x, ldx, w, bias, residual, relu, y, ldy);
+  return abx::launch_linear_simt((cudaStream_t)stream, M, Nout, K, x, ldx, w, bias, residual, relu, y, ldy);
+}
+
+extern "C" int abx_set_gemm_backend(int backend) {
+  ABX_REQUIRE(backend >= 0 && backend <= 2, "abx_set_gemm_backend: 0 auto, 1 SIMT, 2 tcgen05");
+  abx::g_backend = backend;
+  return ABX_OK;
 }

@@ -41,6 +41,8 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _i, _vp, _vp]),
     'abx_igso3_build_tables': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'abx_linear_f32': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i]),
+    'abx_gemm_tf32x3': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i]),
+    'abx_set_gemm_backend': (_i, [_i]),
     'abx_ipa_workspace_bytes': (_sz, [_i, _i]),
     'abx_ipa_pair_bias': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     'abx_ipa_forward': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(IpaWeights), _vp, _vp, _vp, _vp, _sz]),
@@ -84,6 +86,15 @@ def ptr(t, dtype=None):
         raise AbxError('abx_b200 kernels take contiguous tensors')
     if dtype is not None and t.dtype != dtype:
         raise AbxError(f'expected {dtype}, got {t.dtype}')
+    return t.data_ptr()
+
+
+def ptr_any(t):
+    """Device pointer of a CUDA tensor whose rows may be strided (last dim contiguous)."""
+    if not t.is_cuda:
+        raise AbxError('abx_b200 kernels take CUDA tensors only (no CPU fallback)')
+    if t.stride(-1) != 1:
+        raise AbxError('innermost dimension must be contiguous')
     return t.data_ptr()
 
 

@@ -1,0 +1,44 @@
+"""Thin torch-tensor wrappers over the C-ABI dense-layer kernels (include/abx_b200.h).
+
+`linear` is the drop-in for `torch.nn.functional.linear` on CUDA fp32 tensors used by the model modules:
+y = act(x W^T + b) (+ residual) on the tcgen05 3xTF32 GEMM (fp32-level accuracy).  No CPU fallback.
+"""
+import torch
+
+from abx_b200 import lib
+
+ACT = {None: 0, 'none': 0, 'relu': 1, 'gate': 2, 'sigmoid': 3}
+
+
+def linear(x, weight, bias=None, act=None, residual=None, gate=None, out=None, tile_n=0):
+    """x [..., K] (last dim contiguous, uniform row stride), weight [Nout, K] -> [..., Nout].
+
+    act: None | 'relu' | 'sigmoid' | 'gate' (y = (xW^T + b) * sigmoid(gate), gate [..., Nout])
+    residual [..., Nout] is added after the activation."""
+    L = lib.load()
+    K = x.shape[-1]
+    Nout = weight.shape[0]
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    if x2.dtype != torch.float32:
+        x2 = x2.float()
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 4 != 0) or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    ldx = x2.stride(0) if M > 1 else K
+    w = weight.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    y = out if out is not None else torch.empty(lead + (Nout,), device=x.device, dtype=torch.float32)
+    res = residual.reshape(-1, Nout).contiguous() if residual is not None else None
+    g = gate.reshape(-1, Nout).contiguous() if gate is not None else None
+    with lib.device_guard(x2):
+        lib.check(L.abx_gemm_tf32x3(lib.stream(), M, Nout, K, lib.ptr_any(x2), ldx, lib.ptr(w, torch.float32), K,
+                                    lib.ptr(bias.detach() if bias is not None else None), lib.ptr(res), lib.ptr(g),
+                                    ACT[act], lib.ptr(y), Nout, tile_n))
+    return y
+
+
+def set_gemm_backend(name):
+    """'auto' | 'simt' | 'tcgen05' for the node GEMMs inside abx_ipa_forward."""
+    lib.check(lib.load().abx_set_gemm_backend({'auto': 0, 'simt': 1, 'tcgen05': 2}[name]))

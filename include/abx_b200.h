@@ -113,6 +113,22 @@ int abx_igso3_build_tables(void* stream, int num_sigma, int num_omega, int L, co
 int abx_linear_f32(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w,
                    const float* bias, const float* residual, int relu, float* y, int ldy);
 
+/* Same layer on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM accumulator, TMA-staged
+ * operands) with fp32-level accuracy: every operand is split exactly into TF32 hi + lo parts and
+ * D = A_hi W_lo + A_lo W_hi + A_hi W_hi is accumulated in fp32 (3xTF32).  Used for the node GEMMs of IPA
+ * (folding.py:69-86,130-132), IpaScore (score_network.py:117-137) and the trunk's dense layers
+ * (seqformer.py).   w [Nout, ldw] row-major (nn.Linear layout when ldw == K).
+ *   act: 0 none, 1 relu, 2 y = (acc + bias) * sigmoid(gate[M,ldy]), 3 sigmoid;  residual added last
+ *   requirements: K, ldx, ldw multiples of 4; x, w 16-byte aligned
+ *   tile_n: output tile width 32/64/128, 0 = chosen from the problem shape */
+int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                    const float* bias, const float* residual, const float* gate, int act, float* y, int ldy,
+                    int tile_n);
+
+/* Which GEMM the IPA pipeline uses for its node layers: 0 auto (tcgen05 when operands qualify),
+ * 1 SIMT (abx_linear_f32), 2 tcgen05 only.  Process-wide; meant for A/B measurements and tests. */
+int abx_set_gemm_backend(int backend);
+
 /* ---- Invariant Point Attention ---------------------------------------------------------------- */
 /* Weights of abx.model.folding.InvariantPointAttention (folding.py:23-45), reference state_dict
  * layout (out_features x in_features, row-major). */

@@ -1,0 +1,58 @@
+"""GPU parity of the tcgen05 3xTF32 GEMM (abx_gemm_tf32x3) against a float64 reference: the error must be
+at the level of an fp32 GEMM (the sampler's 1e-4 A budget rules out single-pass TF32)."""
+import pytest
+import torch
+
+from abx_b200.utils.weights import np_randn
+from tests.util import maxabs
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 128, 32), (128, 128, 256), (1400, 1152, 256), (1400, 256, 2112), (37, 6, 256), (129, 20, 128),
+          (700, 768, 192), (1000, 192, 768), (33, 40, 36), (4096, 544, 544)]
+
+
+@pytest.mark.parametrize('tile_n', [0, 32, 64, 128])
+@pytest.mark.parametrize('m,n,k', SHAPES)
+def test_gemm_matches_float64(cuda_device, m, n, k, tile_n):
+    from abx_b200 import ops
+    x, w, b = np_randn(1, m, k).cuda(), np_randn(2, n, k).cuda(), np_randn(3, n).cuda()
+    y = ops.linear(x, w, b, tile_n=tile_n)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    fp32 = torch.nn.functional.linear(x, w, b)            # torch's own fp32 GEMM, for scale
+    err, err32 = maxabs(y.cpu(), ref.cpu()), maxabs(fp32.cpu(), ref.cpu())
+    scale = float(ref.abs().max())
+    assert err < 2e-6 * scale * max(1.0, (k / 256) ** 0.5), (err, err32, scale)
+    assert err < 8 * err32 + 1e-6 * scale, (err, err32)
+
+
+def test_gemm_epilogues(cuda_device):
+    from abx_b200 import ops
+    m, n, k = 300, 200, 192
+    x, w, b, r, g = (np_randn(i, *s).cuda() for i, s in enumerate([(m, k), (n, k), (n,), (m, n), (m, n)]))
+    lin = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    tol = 3e-6 * float(lin.abs().max())
+    assert maxabs(ops.linear(x, w, b, act='relu').cpu(), lin.clamp(min=0).cpu()) < tol
+    assert maxabs(ops.linear(x, w, b, act='relu', residual=r).cpu(), (lin.clamp(min=0) + r.double()).cpu()) < tol
+    assert maxabs(ops.linear(x, w, None, residual=r).cpu(), (lin - b.double() + r.double()).cpu()) < tol
+    assert maxabs(ops.linear(x, w, b, act='gate', gate=g).cpu(), (lin * torch.sigmoid(g.double())).cpu()) < tol
+    assert maxabs(ops.linear(x, w, b, act='sigmoid').cpu(), torch.sigmoid(lin).cpu()) < 5e-6
+
+
+def test_gemm_strided_rows_and_batch_dims(cuda_device):
+    from abx_b200 import ops
+    big = np_randn(5, 3, 50, 320).cuda()
+    x = big[..., 64:256]                                  # row stride 320, offset 64 floats: still TMA-able
+    w = np_randn(6, 96, 192).cuda()
+    y = ops.linear(x, w)
+    ref = torch.nn.functional.linear(x.double(), w.double())
+    assert y.shape == (3, 50, 96)
+    assert maxabs(y.cpu(), ref.cpu()) < 2e-6 * float(ref.abs().max())
+
+
+def test_gemm_rejects_bad_arguments(cuda_device):
+    from abx_b200 import lib, ops
+    with pytest.raises(lib.AbxError):
+        ops.linear(torch.zeros(4, 6, device='cuda'), torch.zeros(3, 6, device='cuda'))     # K % 4 != 0
+    with pytest.raises(lib.AbxError):
+        ops.linear(torch.zeros(4, 8), torch.zeros(3, 8))                                   # CPU tensors
