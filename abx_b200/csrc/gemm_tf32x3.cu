@@ -7,15 +7,19 @@
 //     D = A_hi B_lo + A_lo B_hi + A_hi B_hi        (3xTF32; dropped A_lo B_lo term <= 2^-22 relative)
 // accumulates in fp32 in tensor memory.
 //
-// One CTA per 128 x BN output tile, 6 warps:
-//   warp 0      TMA producer: cp.async.bulk.tensor (128-byte swizzle) of the raw fp32 A / W k-slabs
-//               (128 x 32 and BN x 32 elements) into a shared-memory ring
-//   warp 1      allocates TMEM; one elected lane issues 3 x 4 tcgen05.mma.kind::tf32 per slab and commits
-//               to the slab's `empty` barrier (and to `acc_full` after the last slab)
-//   warps 2-5   converters: split each landed slab into hi (in place) / lo (second buffer), fence the
-//               generic-proxy writes for the async proxy, arrive on `conv`; after the main loop the same
-//               warps read the accumulator with tcgen05.ld (warp w owns TMEM lanes 32 (w%4) ..) and apply
-//               the epilogue (bias, activation, residual) before storing.
+// Persistent CTAs (one per SM) walk the 128 x BN output tiles; 16 warps in four role-aligned warpgroups
+// (register budgets re-balanced with setmaxnreg):
+//   WG0  warp 0: TMA producer — cp.async.bulk.tensor (128-byte swizzle) of the raw fp32 A / W k-slabs
+//                (128 x 32 and BN x 32 elements) into a shared-memory ring
+//        warp 1: allocates TMEM; one lane issues 3 x 4 tcgen05.mma.kind::tf32 per slab into one of two TMEM
+//                partial-sum buffers and commits to the slab's `empty` and the buffer's `acc_ready` barriers
+//   WG1  converters: write the lo tile of each landed slab (the tensor core ignores the 13 low mantissa bits
+//        of a tf32 operand, so the raw tile already is the hi part), fence generic->async proxy, arrive `conv`
+//   WG2, WG3  accumulator warpgroups, alternating tiles (ping-pong): per slab read the partial sum with
+//        tcgen05.ld (warp w owns TMEM lanes 32 (w%4)..) and add it to register accumulators with
+//        round-to-nearest — the tensor core itself accumulates with truncation, which over K/8 chained steps
+//        would bias the result by ~K/8 ulp — then run the epilogue (bias, activation, gate, row scale,
+//        residual) straight from registers while the other warpgroup accumulates the next tile.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -26,16 +30,16 @@ namespace abx {
 namespace {
 
 constexpr int kBM = 128, kBK = 32;             // 32 fp32 = one 128-byte swizzle row
-constexpr int kThreads = 320, kConvThreads = 128, kAccThreads = 128;
+constexpr int kThreads = 512, kConvThreads = 128, kAccThreads = 128;
+constexpr int kRegsCtl = 40, kRegsConv = 72, kRegsAcc = 184;   // 128*(40+72) + 256*184 <= 65536
 constexpr uint32_t kTileABytes = kBM * kBK * 4;
 
 template <int BN> struct GemmCfg {
   static constexpr uint32_t kTileBBytes = BN * kBK * 4;
   static constexpr uint32_t kStageBytes = 2 * (kTileABytes + kTileBBytes);     // raw/hi + lo for A and B
   static constexpr int kStages = BN >= 128 ? 3 : (BN >= 64 ? 4 : 5);
-  static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;             // two partial-sum buffers
-  static constexpr uint32_t kStoreBytes = 4 * 32 * 36 * 4;                     // per-warp 32x36 transpose tiles
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStoreBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr uint32_t kTmemCols = 4 * BN;                                // two partial-sum buffers per accumulator WG
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,65 +115,71 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 struct Epilogue {
   const float* bias;       // [Nout] or null
-  const float* residual;   // [M, ldy] or null (added after the activation)
-  const float* gate;       // [M, ldy] or null: y = (acc + bias) * sigmoid(gate)   (act == 2)
-  int act;                 // 0 none, 1 relu, 2 multiply by sigmoid(gate), 3 sigmoid
+  const float* residual;   // [M, ldy] or null (added last)
+  const float* gate;       // [M, ldy]: act 2: v * sigmoid(gate);  act 4: sigmoid(v) * gate
+  const float* row_scale;  // [M] or null: multiplies the activated value (pair / sequence masks)
+  int act;                 // 0 none, 1 relu, 2 v * sigmoid(gate), 3 sigmoid(v), 4 sigmoid(v) * gate
 };
 
 template <int ACT>
-__device__ __forceinline__ float epilogue_op(float a, float bias, float gate, float res) {
+__device__ __forceinline__ float epilogue_op(float a, float bias, float gate, float scale, float res) {
   a += bias;
   if (ACT == 1) a = fmaxf(a, 0.f);
   else if (ACT == 2) a = a * (1.f / (1.f + expf(-gate)));
   else if (ACT == 3) a = 1.f / (1.f + expf(-a));
-  return a + res;
+  else if (ACT == 4) a = gate * (1.f / (1.f + expf(-a)));
+  return a * scale + res;
 }
 
-// One 32 x 32 block of the output tile from the warp's smem transpose tile: lane = (row group lane/8, 4 columns
-// 4 (lane%8)), 8 passes of 4 rows; all loads are issued before the stores of a pass.
-template <int ACT>
-__device__ __forceinline__ void store_chunk(const float* st, const Epilogue& ep, float* __restrict__ y, int ldy, int row0,
-                                            int col0, int M, int Nout, int lane, bool vec_ok) {
-  const int rg = lane >> 3, col = col0 + 4 * (lane & 7);
-  float bv[4] = {0.f, 0.f, 0.f, 0.f};
-  if (ep.bias) {
+// Epilogue of one output row held by this lane: acc[0..BN) are columns n0.. of row `row`.  Each lane streams
+// its own row in 16-column pieces (4 x 16-byte stores; gate / residual pieces are loaded first).
+template <int ACT, int BN>
+__device__ __forceinline__ void store_row(const float (&acc)[BN], const Epilogue& ep, float* __restrict__ y, int ldy,
+                                          int row, int n0, int Nout, bool vec_ok) {
+  const size_t ro = (size_t)row * ldy;
+  const float sc = ep.row_scale ? __ldg(ep.row_scale + row) : 1.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) bv[u] = (col + u < Nout) ? __ldg(ep.bias + col + u) : 0.f;
-  }
-  const bool full4 = vec_ok && (col + 3 < Nout);
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    const int col = n0 + c0;
+    if (col >= Nout) break;
+    if (vec_ok && col + 15 < Nout) {
+      float4 g[4], r[4];
+      if (ACT == 2 || ACT == 4) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-  float4 v[4];
+        for (int u = 0; u < 4; ++u) g[u] = *reinterpret_cast<const float4*>(ep.gate + ro + col + 4 * u);
+      }
+      if (ep.residual) {
 #pragma unroll
-  for (int p = 0; p < 4; ++p) v[p] = *reinterpret_cast<const float4*>(st + (16 * h + 4 * p + rg) * 36 + 4 * (lane & 7));
+        for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const float4*>(ep.residual + ro + col + 4 * u);
+      } else {
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int row = row0 + 16 * h + 4 * p + rg;
-    if (row >= M) continue;
-    const size_t o = (size_t)row * ldy + col;
-    float in[4] = {v[p].x, v[p].y, v[p].z, v[p].w}, g[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
-    if (full4) {
-      if (ACT == 2) { float4 t = *reinterpret_cast<const float4*>(ep.gate + o); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
-      if (ep.residual) { float4 t = *reinterpret_cast<const float4*>(ep.residual + o); r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w; }
-      float4 out;
-      out.x = epilogue_op<ACT>(in[0], bv[0], g[0], r[0]);
-      out.y = epilogue_op<ACT>(in[1], bv[1], g[1], r[1]);
-      out.z = epilogue_op<ACT>(in[2], bv[2], g[2], r[2]);
-      out.w = epilogue_op<ACT>(in[3], bv[3], g[3], r[3]);
-      *reinterpret_cast<float4*>(y + o) = out;
-    } else {
+        for (int u = 0; u < 4; ++u) r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        float4 bv = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o;
+        o.x = epilogue_op<ACT>(acc[c0 + 4 * u + 0], bv.x, g[u].x, sc, r[u].x);
+        o.y = epilogue_op<ACT>(acc[c0 + 4 * u + 1], bv.y, g[u].y, sc, r[u].y);
+        o.z = epilogue_op<ACT>(acc[c0 + 4 * u + 2], bv.z, g[u].z, sc, r[u].z);
+        o.w = epilogue_op<ACT>(acc[c0 + 4 * u + 3], bv.w, g[u].w, sc, r[u].w);
+        *reinterpret_cast<float4*>(y + ro + col + 4 * u) = o;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
         if (col + u < Nout) {
-          const float gg = (ACT == 2) ? ep.gate[o + u] : 0.f;
-          const float rr = ep.residual ? ep.residual[o + u] : 0.f;
-          y[o + u] = epilogue_op<ACT>(in[u], bv[u], gg, rr);
+          const float bv = ep.bias ? __ldg(ep.bias + col + u) : 0.f;
+          const float gg = (ACT == 2 || ACT == 4) ? ep.gate[ro + col + u] : 0.f;
+          const float rr = ep.residual ? ep.residual[ro + col + u] : 0.f;
+          y[ro + col + u] = epilogue_op<ACT>(acc[c0 + u], bv, gg, sc, rr);
         }
       }
     }
   }
-  }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -183,14 +193,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   auto stage_alo = [&](int s) { return stage_a(s) + kTileABytes; };
   auto stage_b = [&](int s) { return stage_a(s) + 2 * kTileABytes; };
   auto stage_blo = [&](int s) { return stage_b(s) + Cfg::kTileBBytes; };
-  float* store_stage = reinterpret_cast<float*>(smem + (size_t)kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * Cfg::kStageBytes + Cfg::kStoreBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * Cfg::kStageBytes);
   uint64_t* full = bars;                        // TMA -> converters
   uint64_t* conv = bars + kStages;              // converters -> MMA
   uint64_t* empty = bars + 2 * kStages;         // MMA -> TMA
-  uint64_t* acc_ready = bars + 3 * kStages;     // [2] MMA -> accumulator warps (partial sum of one k-slab in TMEM)
-  uint64_t* acc_free = bars + 3 * kStages + 2;  // [2] accumulator warps -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
+  uint64_t* acc_ready = bars + 3 * kStages;     // [2 WGs][2] MMA -> accumulator WG (partial sum of one k-slab in TMEM)
+  uint64_t* acc_free = bars + 3 * kStages + 4;  // [2 WGs][2] accumulator WG -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + kBK - 1) / kBK;
@@ -205,7 +214,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(conv + s, kConvThreads);
       mbar_init(empty + s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(acc_ready + b, 1);
       mbar_init(acc_free + b, kAccThreads);
     }
@@ -221,11 +230,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // Every role walks the same static schedule: tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs
-  // running side by side share the A rows in L2); `it` counts k-slabs across tiles and drives stages / phases.
-  if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
+  // Every role walks the same static schedule: this CTA's j-th tile is blockIdx.x + j gridDim.x (n fastest, so
+  // CTAs running side by side share the A rows in L2); `it` = j nkb + kb counts k-slabs and drives the smem
+  // stages, the two TMEM partial-sum buffers and all barrier phases.  Tile j belongs to accumulator WG j & 1.
+  const int wg = warp >> 2;
+  if (wg == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
+    if (warp == 0 && lane == 0) {
+      // ---------------- TMA producer ----------------
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int m0 = (tile / nt) * kBM, n0 = (tile % nt) * BN;
@@ -238,20 +250,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tma_load_2d(stage_b(s), &map_b, full + s, kb * kBK, n0);
         }
       }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    // The tensor core adds into its fp32 accumulator with truncation; chaining all K/8 steps in TMEM would
-    // bias the result by ~K/8 ulp.  So each k-slab (12 MMAs) starts a fresh partial sum in one of two TMEM
-    // buffers, and the accumulator warps add the partials in registers with round-to-nearest.
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
+      // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+      uint32_t it = 0, lit[2] = {0, 0};               // lit[g]: k-slabs issued so far for accumulator WG g
+      int j = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
+        const int g = j & 1;
+        for (int kb = 0; kb < nkb; ++kb, ++it, ++lit[g]) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          const uint32_t buf = it & 1, use = it >> 1;
+          const uint32_t buf = 2 * g + (lit[g] & 1), use = lit[g] >> 1;
           mbar_wait(acc_free + buf, (use & 1) ^ 1);
           mbar_wait(conv + s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -271,9 +280,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
       }
     }
-  } else if (warp < 6) {
-    // ---------------- converters: raw fp32 slab -> hi (in place) + lo ----------------
-    const int ct = threadIdx.x - 64;                 // 0..127
+  } else if (wg == 1) {
+    // ---------------- converters: raw fp32 slab -> lo tile (hi = the raw tile, low bits ignored) ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConv));
+    const int ct = threadIdx.x - 128;                // 0..127
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -292,27 +302,41 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         };
         float4* a = reinterpret_cast<float4*>(stage_a(s));
         float4* alo = reinterpret_cast<float4*>(stage_alo(s));
-#pragma unroll 4
+#pragma unroll 8
         for (int i = ct; i < (int)(kTileABytes / 16); i += kConvThreads) split(a, alo, i);
         float4* b = reinterpret_cast<float4*>(stage_b(s));
         float4* blo = reinterpret_cast<float4*>(stage_blo(s));
-#pragma unroll 4
+#pragma unroll 8
         for (int i = ct; i < (int)(Cfg::kTileBBytes / 16); i += kConvThreads) split(b, blo, i);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(conv + s);
       }
     }
   } else {
-    // ---------------- accumulator / epilogue warps (6..9): thread = one output row ----------------
+    // ---------------- accumulator / epilogue warpgroups (ping-pong on tiles): lane = one output row ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsAcc));
+    const int g = wg - 2;
     const int q = warp & 3;                          // TMEM lane quarter this warp may read
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                        (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
+                        (!ep.residual || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) &&
+                        (!ep.gate || (reinterpret_cast<uintptr_t>(ep.gate) & 15) == 0);
+    uint32_t lit = 0;                                // k-slabs this WG has drained (its own phase counter)
+    for (int tile = blockIdx.x + g * gridDim.x; tile < tiles; tile += 2 * gridDim.x) {
       const int m0 = (tile / nt) * kBM, n0 = (tile % nt) * BN;
+      const int row = m0 + 32 * q + lane;
+      if (row < M) {                                 // pull this row's gate / residual pieces into L2 ahead of the epilogue
+        const int ncol = min(BN, Nout - n0);
+        if (ep.gate)
+          for (int c = 0; c < ncol; c += 32) prefetch_l2(ep.gate + (size_t)row * ldy + n0 + c);
+        if (ep.residual)
+          for (int c = 0; c < ncol; c += 32) prefetch_l2(ep.residual + (size_t)row * ldy + n0 + c);
+      }
       float acc[BN];
 #pragma unroll
       for (int c = 0; c < BN; ++c) acc[c] = 0.f;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const uint32_t buf = it & 1, use = it >> 1;
+      for (int kb = 0; kb < nkb; ++kb, ++lit) {
+        const uint32_t buf = 2 * g + (lit & 1), use = lit >> 1;
         mbar_wait(acc_ready + buf, use & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -325,26 +349,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(acc_free + buf);
       }
-      // epilogue: transpose 32x32 blocks through a per-warp smem tile (row stride 36 floats: conflict-free
-      // float4 writes by row and float4 reads by 8-lane row groups) so a warp stores 4 x 128-byte row pieces
-      float* st = store_stage + q * (32 * 36);
-      const int row0 = m0 + 32 * q;
-      const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
-                          (!ep.residual || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) &&
-                          (!ep.gate || (reinterpret_cast<uintptr_t>(ep.gate) & 15) == 0);
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= Nout) break;
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          *reinterpret_cast<float4*>(st + lane * 36 + c) = make_float4(acc[c0 + c], acc[c0 + c + 1], acc[c0 + c + 2], acc[c0 + c + 3]);
-        __syncwarp();
+      if (row < M) {
         switch (ep.act) {
-          case 0: store_chunk<0>(st, ep, y, ldy, row0, n0 + c0, M, Nout, lane, vec_ok); break;
-          case 1: store_chunk<1>(st, ep, y, ldy, row0, n0 + c0, M, Nout, lane, vec_ok); break;
-          case 2: store_chunk<2>(st, ep, y, ldy, row0, n0 + c0, M, Nout, lane, vec_ok); break;
-          default: store_chunk<3>(st, ep, y, ldy, row0, n0 + c0, M, Nout, lane, vec_ok); break;
+          case 0: store_row<0, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
+          case 1: store_row<1, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
+          case 2: store_row<2, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
+          case 3: store_row<3, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
+          default: store_row<4, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
         }
       }
     }
@@ -436,15 +447,16 @@ bool gemm_tf32x3_supported(int M, int Nout, int K, const float* x, int ldx, cons
          (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
 }
 
-// act: 0 none, 1 relu, 2 multiply by sigmoid(gate[M,ldy]), 3 sigmoid.  tile_n: 0 = choose, else 32/64/128.
+// act: see Epilogue.  tile_n: 0 = choose, else 32/64/128.
 int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
-                       const float* bias, const float* residual, const float* gate, int act, float* y, int ldy, int tile_n) {
-  Epilogue ep{bias, residual, gate, act};
+                       const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
+                       float* y, int ldy, int tile_n) {
+  Epilogue ep{bias, residual, gate, row_scale, act};
   if (tile_n == 0) {
     // enough CTAs to cover the 148 SMs beats wide tiles for the small-M node GEMMs
     const int mt = ceil_div(M, kBM);
-    if (Nout <= 32 || mt * ceil_div(Nout, 64) < 120) tile_n = 32;
-    else if (Nout <= 64 || mt * ceil_div(Nout, 128) < 120) tile_n = 64;
+    if (Nout <= 32 || mt * ceil_div(Nout, 64) < 100) tile_n = 32;
+    else if (Nout <= 64 || mt * ceil_div(Nout, 128) < 100) tile_n = 64;
     else tile_n = 128;
   }
   switch (tile_n) {
@@ -459,13 +471,14 @@ int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, i
 }  // namespace abx
 
 extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
-                               const float* bias, const float* residual, const float* gate, int act, float* y, int ldy,
-                               int tile_n) {
+                               const float* bias, const float* residual, const float* gate, const float* row_scale,
+                               int act, float* y, int ldy, int tile_n) {
   ABX_REQUIRE(M > 0 && Nout > 0 && K > 0 && x && w && y, "abx_gemm_tf32x3: bad shape or null argument");
   ABX_REQUIRE(abx::gemm_tf32x3_supported(M, Nout, K, x, ldx, w, ldw),
               "abx_gemm_tf32x3: K, ldx, ldw must be multiples of 4 with ldx, ldw >= K, and x, w 16-byte aligned "
               "(K=%d ldx=%d ldw=%d)", K, ldx, ldw);
   ABX_REQUIRE(ldy >= Nout, "abx_gemm_tf32x3: ldy < Nout");
-  ABX_REQUIRE(act >= 0 && act <= 3 && (act != 2 || gate), "abx_gemm_tf32x3: bad activation / missing gate");
-  return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, residual, gate, act, y, ldy, tile_n);
+  ABX_REQUIRE(act >= 0 && act <= 4 && ((act != 2 && act != 4) || gate), "abx_gemm_tf32x3: bad activation / missing gate");
+  return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, residual, gate, row_scale, act, y,
+                                 ldy, tile_n);
 }

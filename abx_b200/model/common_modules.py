@@ -33,10 +33,46 @@ def as_config(c):
     return c
 
 
+class AbxLinear(nn.Linear):
+    """nn.Linear (same parameters / state_dict keys) whose forward runs on the tcgen05 3xTF32 GEMM
+    (abx_gemm_tf32x3) with the activation / gate / mask / residual of the surrounding reference code fused
+    into the epilogue.  CUDA tensors only; layers whose input width is not a multiple of 4 (two small
+    once-per-complex encoder layers) use torch's CUDA matmul."""
+
+    def forward(self, x, act=None, residual=None, gate=None, row_scale=None):
+        from abx_b200 import ops
+        if self.in_features % 4 != 0:
+            if not x.is_cuda:
+                raise ops.lib.AbxError('abx_b200 layers take CUDA tensors only (no CPU fallback)')
+            assert act in (None, 'relu') and gate is None and row_scale is None
+            y = torch.nn.functional.linear(x, self.weight, self.bias)
+            y = torch.relu(y) if act == 'relu' else y
+            return y if residual is None else y + residual
+        return ops.linear(x, self.weight, self.bias, act=act, residual=residual, gate=gate, row_scale=row_scale)
+
+
+def mlp(seq, x, residual=None):
+    """Run an nn.Sequential of (LayerNorm | AbxLinear | ReLU) with every ReLU fused into the preceding
+    GEMM's epilogue and `residual` into the last one.  Module indices (state_dict keys) are untouched."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, AbxLinear):
+            relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            last = i + (2 if relu else 1) >= len(mods)
+            x = m(x, act='relu' if relu else None, residual=residual if last else None)
+            i += 2 if relu else 1
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
 def Linear(input_dim, output_dim, init='linear', bias=True, config=None):
-    """nn.Linear with the AF2-style initialisers of common_modules.py:11-38."""
+    """AbxLinear with the AF2-style initialisers of common_modules.py:11-38."""
     assert init in ('gate', 'final', 'attn', 'relu', 'linear')
-    layer = nn.Linear(input_dim, output_dim, bias=bias)
+    layer = AbxLinear(input_dim, output_dim, bias=bias)
     with torch.no_grad():
         if init in ('gate', 'final'):
             layer.weight.zero_()

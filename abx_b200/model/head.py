@@ -9,7 +9,7 @@ from torch import nn
 
 from abx_b200.data import residue_tables as rt
 from abx_b200.model import atom, quat_affine
-from abx_b200.model.common_modules import LayerNorm, Linear, as_config
+from abx_b200.model.common_modules import LayerNorm, Linear, as_config, mlp
 from abx_b200.model.score_network import IpaScore
 
 
@@ -66,7 +66,7 @@ class SequenceHead(nn.Module):
     def forward(self, headers, representations, batch):
         """head.py:162-201."""
         fold = headers['folding']
-        logits = self.net(fold['representations']['structure_module'])
+        logits = mlp(self.net, fold['representations']['structure_module'])
         seq_0 = torch.argmax(logits, dim=-1)            # == argmax of the softmax (head.py:165-166)
         fixed_mask = batch['fixed_mask']
         seq_0 = seq_0 * (1 - fixed_mask) + batch['seq_t'] * fixed_mask
@@ -89,7 +89,7 @@ class PredictedLDDTHead(nn.Module):
         self.config = config
 
     def forward(self, headers, representations, batch):
-        logits = self.net(headers['folding']['representations']['structure_module'])
+        logits = mlp(self.net, headers['folding']['representations']['structure_module'])
         return dict(logits=logits, pLDDT=plddt(logits))
 
 

@@ -12,7 +12,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from abx_b200.model import quat_affine, r3
-from abx_b200.model.common_modules import LayerNorm, Linear, as_config
+from abx_b200.model.common_modules import LayerNorm, Linear, as_config, mlp
 from abx_b200.model.folding import InvariantPointAttention as IPA
 from abx_b200.model.sidechain import MultiRigidSidechain
 
@@ -79,7 +79,7 @@ class IpaScore(nn.Module):
             seq_act = self.attention_module(inputs_1d=seq_act, inputs_2d=static_pair_act, mask=node_mask,
                                             in_rigids=(curr_rots, curr_trans), pair_bias=pair_bias, residual=seq_act)
             seq_act = self.attention_layer_norm(seq_act)
-            seq_act = self.transition_layer_norm(seq_act + self.transition_module(seq_act))
+            seq_act = self.transition_layer_norm(mlp(self.transition_module, seq_act, residual=seq_act))
 
             quaternion_update, translation_update = self.affine_update(seq_act).chunk(2, dim=-1)
             delta_quat = quat_affine.quat_precompose_vec(delta_quat, quaternion_update)

@@ -12,7 +12,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from abx_b200.model.common_modules import LayerNorm, Linear, as_config
+from abx_b200.model.common_modules import LayerNorm, Linear, as_config, mlp
 from abx_b200.model.encoder import PairEmbedding, ResidueEmbedding
 
 RESTYPE_NUM, NUM_AB_REGIONS = 20, 14
@@ -45,12 +45,27 @@ class Attention(nn.Module):
         self.gate = Linear(input_dim, value_dim, init='gate')
         self.proj_out = Linear(value_dim, input_dim, init='final')
 
-    def forward(self, q_data, k_data=None, bias=None, k_mask=None):
-        """q_data [B,S,L,C]; bias [B,H,L,L] (shared over S); k_mask [B,S|1,L] bool."""
+    def _qkv_weight(self):
+        """[Wq; Wk; Wv] as one [3*dim, C] operand so self-attention projects q, k, v in a single GEMM."""
+        ws = (self.proj_q.weight, self.proj_k.weight, self.proj_v.weight)
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if getattr(self, '_qkv_cache', (None,))[0] != key:
+            self._qkv_cache = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
+        return self._qkv_cache[1]
+
+    def forward(self, q_data, k_data=None, bias=None, k_mask=None, residual=None):
+        """q_data [B,S,L,C]; bias [B,H,L,L] (shared over S); k_mask [B,S|1,L] bool.
+        `residual` [B,S,L,C] is added in the output projection's epilogue."""
+        from abx_b200 import ops
         H = self.num_head
         if self.split_first:
-            q, k, v = self.proj_q(q_data), self.proj_k(k_data), self.proj_v(k_data)
-            q, k, v = (x.reshape(x.shape[:-1] + (H, -1)).transpose(-2, -3) for x in (q, k, v))        # b s h l d
+            if k_data is None or k_data is q_data:
+                t = ops.linear(q_data, self._qkv_weight())
+                t = t.reshape(t.shape[:-1] + (3, H, -1))
+                q, k, v = (t[..., i, :, :].transpose(-2, -3) for i in range(3))                       # b s h l d
+            else:
+                q, k, v = self.proj_q(q_data), self.proj_k(k_data), self.proj_v(k_data)
+                q, k, v = (x.reshape(x.shape[:-1] + (H, -1)).transpose(-2, -3) for x in (q, k, v))
         else:
             t = self.proj_in(q_data)
             t = t.reshape(t.shape[:-1] + (H, -1)).transpose(-2, -3)
@@ -60,7 +75,8 @@ class Attention(nn.Module):
         add = add.masked_fill(~k_mask[:, :, None, None, :].bool(), neg) if k_mask is not None else add
         o = F.scaled_dot_product_attention(q, k, v, attn_mask=add.expand(q.shape[:-1] + (k.shape[-2],)))
         o = o.transpose(-2, -3).reshape(q_data.shape[:-1] + (-1,))
-        return self.proj_out(o * torch.sigmoid(self.gate(q_data)))
+        gated = self.gate(q_data, act='sigmoid_mul', gate=o)                  # sigmoid(gate(q)) * o in the epilogue
+        return self.proj_out(gated, residual=residual)
 
 
 class SeqAttentionWithPairBias(nn.Module):
@@ -73,10 +89,11 @@ class SeqAttentionWithPairBias(nn.Module):
                               split_first=False)
         self.config = config
 
-    def forward(self, seq_act, pair_act, mask):
+    def forward(self, seq_act, pair_act, mask, residual=None):
         s = self.seq_norm(seq_act)
         bias = self.proj_pair(self.pair_norm(pair_act)).permute(0, 3, 1, 2)
-        return self.attn(s[:, None], bias=bias, k_mask=mask[:, None, :])[:, 0]
+        res = residual[:, None] if residual is not None else None
+        return self.attn(s[:, None], bias=bias, k_mask=mask[:, None, :], residual=res)[:, 0]
 
 
 class Transition(nn.Module):
@@ -86,8 +103,9 @@ class Transition(nn.Module):
         self.transition = nn.Sequential(LayerNorm(num_in_channel), Linear(num_in_channel, inter, init='linear'), nn.ReLU(),
                                         Linear(inter, num_in_channel, init='final'))
 
-    def forward(self, act, mask=None):
-        return self.transition(act)
+    def forward(self, act, mask=None, residual=None):
+        """LN -> Linear+ReLU -> Linear (+ residual), the ReLU and the residual in the GEMM epilogues."""
+        return mlp(self.transition, act, residual=residual)
 
 
 class OuterProductMean(nn.Module):
@@ -99,14 +117,14 @@ class OuterProductMean(nn.Module):
         self.right_proj = Linear(num_in_channel, c.num_outer_channel, init='linear')
         self.out_proj = Linear(2 * c.num_outer_channel, num_out_channel, init='final')
 
-    def forward(self, act, mask):
-        """seqformer.py:378-411: concat(left_j * right_i, left_j - right_i) -> out_proj."""
-        m = mask[:, :, None].to(act.dtype)
+    def forward(self, act, mask, residual=None):
+        """seqformer.py:378-411: concat(left_j * right_i, left_j - right_i) -> out_proj (+ residual)."""
+        m = mask.to(act.dtype)
         a = self.norm(act)
-        left, right = m * self.left_proj(a), m * self.right_proj(a)
+        left, right = self.left_proj(a, row_scale=m), self.right_proj(a, row_scale=m)
         prod = left[:, None, :, :] * right[:, :, None, :]
         diff = left[:, None, :, :] - right[:, :, None, :]
-        return self.out_proj(torch.cat([prod, diff], dim=-1))
+        return self.out_proj(torch.cat([prod, diff], dim=-1), residual=residual)
 
 
 class TriangleMultiplication(nn.Module):
@@ -125,20 +143,20 @@ class TriangleMultiplication(nn.Module):
         self.outgoing = c.orientation == 'per_row'
         self.config = c
 
-    def forward(self, act, mask):
-        """seqformer.py:413-504."""
-        pm = (mask[:, :, None] * mask[:, None, :])[..., None].to(act.dtype)
+    def forward(self, act, mask, residual=None):
+        """seqformer.py:413-504.  Gates, pair mask and the residual ride in GEMM epilogues."""
+        pm = (mask[:, :, None] * mask[:, None, :]).to(act.dtype)
         act = self.norm(act)
-        left = pm * self.left_proj(act) * torch.sigmoid(self.left_gate(act))
-        right = pm * self.right_proj(act) * torch.sigmoid(self.right_gate(act))
+        left = self.left_proj(act, act='gate', gate=self.left_gate(act), row_scale=pm)
+        right = self.right_proj(act, act='gate', gate=self.right_gate(act), row_scale=pm)
         # channel-major so the triangle product is one batched GEMM per channel
         lt, rt_ = left.permute(0, 3, 1, 2), right.permute(0, 3, 1, 2)                 # b c i k
         if self.outgoing:
             out = torch.matmul(lt, rt_.transpose(-1, -2))                            # sum_k l[i,k] r[j,k]
         else:
             out = torch.matmul(lt.transpose(-1, -2), rt_)                            # sum_k l[k,i] r[k,j]
-        out = self.proj_out(self.final_norm(out.permute(0, 2, 3, 1)))
-        return out * torch.sigmoid(self.final_gate(act))
+        return self.proj_out(self.final_norm(out.permute(0, 2, 3, 1)), act='gate', gate=self.final_gate(act),
+                             residual=residual)
 
 
 class TriangleAttention(nn.Module):
@@ -152,14 +170,17 @@ class TriangleAttention(nn.Module):
         self.per_column = c.orientation == 'per_column'
         self.config = c
 
-    def forward(self, pair_act, seq_mask):
-        """seqformer.py:506-550."""
+    def forward(self, pair_act, seq_mask, residual=None):
+        """seqformer.py:506-550 (+ residual, fused for the per-row orientation)."""
         if self.per_column:
-            pair_act = pair_act.transpose(1, 2)
-        pair_act = self.norm(pair_act)
-        bias = self.proj_pair(pair_act).permute(0, 3, 1, 2)
-        out = self.attn(pair_act, pair_act, bias=bias, k_mask=seq_mask[:, None, :])
-        return out.transpose(1, 2) if self.per_column else out
+            x = self.norm(pair_act).transpose(1, 2).contiguous()
+        else:
+            x = self.norm(pair_act)
+        bias = self.proj_pair(x).permute(0, 3, 1, 2)
+        if self.per_column:
+            out = self.attn(x, x, bias=bias, k_mask=seq_mask[:, None, :]).transpose(1, 2)
+            return out if residual is None else residual + out
+        return self.attn(x, x, bias=bias, k_mask=seq_mask[:, None, :], residual=residual)
 
 
 class SeqformerIteration(nn.Module):
@@ -178,15 +199,15 @@ class SeqformerIteration(nn.Module):
 
     def forward(self, seq_act, pair_act, seq_mask):
         """seqformer.py:569-606 (inference: dropout is the identity)."""
-        seq_act = seq_act + self.seq_attn(seq_act, pair_act, seq_mask)
-        seq_act = seq_act + self.seq_transition(seq_act)
-        pair_act = pair_act + self.outer_product_mean(seq_act, seq_mask)
+        seq_act = self.seq_attn(seq_act, pair_act, seq_mask, residual=seq_act)
+        seq_act = self.seq_transition(seq_act, residual=seq_act)
+        pair_act = self.outer_product_mean(seq_act, seq_mask, residual=pair_act)
         mf = seq_mask.to(pair_act.dtype)
-        pair_act = pair_act + self.triangle_multiplication_outgoing(pair_act, mf)
-        pair_act = pair_act + self.triangle_multiplication_incoming(pair_act, mf)
-        pair_act = pair_act + self.triangle_attention_starting_node(pair_act, seq_mask)
-        pair_act = pair_act + self.triangle_attention_ending_node(pair_act, seq_mask)
-        pair_act = pair_act + self.pair_transition(pair_act)
+        pair_act = self.triangle_multiplication_outgoing(pair_act, mf, residual=pair_act)
+        pair_act = self.triangle_multiplication_incoming(pair_act, mf, residual=pair_act)
+        pair_act = self.triangle_attention_starting_node(pair_act, seq_mask, residual=pair_act)
+        pair_act = self.triangle_attention_ending_node(pair_act, seq_mask, residual=pair_act)
+        pair_act = self.pair_transition(pair_act, residual=pair_act)
         return seq_act, pair_act
 
 

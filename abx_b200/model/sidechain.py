@@ -4,7 +4,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from abx_b200.model import atom
-from abx_b200.model.common_modules import Linear
+from abx_b200.model.common_modules import Linear, mlp
 from abx_b200.model.quat_affine import l2_normalize
 
 
@@ -14,7 +14,7 @@ class ResNetBlock(nn.Module):
         self.net = nn.Sequential(nn.ReLU(), Linear(dim, dim, init='relu'), nn.ReLU(), Linear(dim, dim, init='final'))
 
     def forward(self, act):
-        return act + self.net(act)
+        return mlp(self.net, act, residual=act)
 
 
 class TorsionModule(nn.Module):

@@ -7,14 +7,14 @@ import torch
 
 from abx_b200 import lib
 
-ACT = {None: 0, 'none': 0, 'relu': 1, 'gate': 2, 'sigmoid': 3}
+ACT = {None: 0, 'none': 0, 'relu': 1, 'gate': 2, 'sigmoid': 3, 'sigmoid_mul': 4}
 
 
-def linear(x, weight, bias=None, act=None, residual=None, gate=None, out=None, tile_n=0):
+def linear(x, weight, bias=None, act=None, residual=None, gate=None, row_scale=None, out=None, tile_n=0):
     """x [..., K] (last dim contiguous, uniform row stride), weight [Nout, K] -> [..., Nout].
 
-    act: None | 'relu' | 'sigmoid' | 'gate' (y = (xW^T + b) * sigmoid(gate), gate [..., Nout])
-    residual [..., Nout] is added after the activation."""
+    v = xW^T + b;  act: None | 'relu' | 'sigmoid' | 'gate' (v * sigmoid(gate)) | 'sigmoid_mul' (sigmoid(v) * gate)
+    with gate [..., Nout];  then y = v * row_scale[...] + residual[..., Nout]."""
     L = lib.load()
     K = x.shape[-1]
     Nout = weight.shape[0]
@@ -32,10 +32,11 @@ def linear(x, weight, bias=None, act=None, residual=None, gate=None, out=None, t
     y = out if out is not None else torch.empty(lead + (Nout,), device=x.device, dtype=torch.float32)
     res = residual.reshape(-1, Nout).contiguous() if residual is not None else None
     g = gate.reshape(-1, Nout).contiguous() if gate is not None else None
+    rs = row_scale.reshape(-1).to(torch.float32).contiguous() if row_scale is not None else None
     with lib.device_guard(x2):
         lib.check(L.abx_gemm_tf32x3(lib.stream(), M, Nout, K, lib.ptr_any(x2), ldx, lib.ptr(w, torch.float32), K,
                                     lib.ptr(bias.detach() if bias is not None else None), lib.ptr(res), lib.ptr(g),
-                                    ACT[act], lib.ptr(y), Nout, tile_n))
+                                    lib.ptr(rs), ACT[act], lib.ptr(y), Nout, tile_n))
     return y
 
 

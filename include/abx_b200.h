@@ -118,12 +118,14 @@ int abx_linear_f32(void* stream, int M, int Nout, int K, const float* x, int ldx
  * D = A_hi W_lo + A_lo W_hi + A_hi W_hi is accumulated in fp32 (3xTF32).  Used for the node GEMMs of IPA
  * (folding.py:69-86,130-132), IpaScore (score_network.py:117-137) and the trunk's dense layers
  * (seqformer.py).   w [Nout, ldw] row-major (nn.Linear layout when ldw == K).
- *   act: 0 none, 1 relu, 2 y = (acc + bias) * sigmoid(gate[M,ldy]), 3 sigmoid;  residual added last
+ *   v = acc + bias;  act: 0 none, 1 relu(v), 2 v * sigmoid(gate), 3 sigmoid(v), 4 sigmoid(v) * gate
+ *   (gate [M,ldy]);  then y = v * row_scale[row] + residual   (row_scale [M], residual [M,ldy]; all optional)
+ *   — the gated projections, masked projections and residual adds of seqformer.py fused into the GEMM
  *   requirements: K, ldx, ldw multiples of 4; x, w 16-byte aligned
  *   tile_n: output tile width 32/64/128, 0 = chosen from the problem shape */
 int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
-                    const float* bias, const float* residual, const float* gate, int act, float* y, int ldy,
-                    int tile_n);
+                    const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
+                    float* y, int ldy, int tile_n);
 
 /* Which GEMM the IPA pipeline uses for its node layers: 0 auto (tcgen05 when operands qualify),
  * 1 SIMT (abx_linear_f32), 2 tcgen05 only.  Process-wide; meant for A/B measurements and tests. */

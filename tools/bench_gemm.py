@@ -38,6 +38,12 @@ def main():
         best = min(row[f'abx_bn{tn}_ms'] for tn in (32, 64, 128))
         row['abx_tflops_fp32_equiv'] = 2 * m * n * k / best / 1e9
         row['torch_tflops'] = 2 * m * n * k / row['torch_ms'] / 1e9
+        if m > 100000:
+            g = torch.randn(m, n, device='cuda')
+            r = torch.randn(m, n, device='cuda')
+            row['abx_gate_res_ms'] = time_ms(lambda: ops.linear(x, w, b, act='gate', gate=g, residual=r, out=y))
+            row['abx_res_ms'] = time_ms(lambda: ops.linear(x, w, b, residual=r, out=y))
+            del g, r
         ref = torch.nn.functional.linear(x[:2048].double(), w.double(), b.double())
         row['abx_maxerr'] = float((ops.linear(x[:2048], w, b).double() - ref).abs().max())
         row['torch_maxerr'] = float((torch.nn.functional.linear(x[:2048], w, b).double() - ref).abs().max())
