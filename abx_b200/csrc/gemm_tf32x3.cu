@@ -119,6 +119,8 @@ struct Epilogue {
   const float* gate;       // [M, ldy]: act 2: v * sigmoid(gate);  act 4: sigmoid(v) * gate
   const float* row_scale;  // [M] or null: multiplies the activated value (pair / sequence masks)
   int act;                 // 0 none, 1 relu, 2 v * sigmoid(gate), 3 sigmoid(v), 4 sigmoid(v) * gate
+  int transpose_n;         // n > 0: rows are (b,i,j) of a [B,n,n,*] tensor and row (b,i,j) is stored to (b,j,i);
+                           // y and residual use the transposed row, gate / row_scale the GEMM's own row
 };
 
 template <int ACT>
@@ -136,7 +138,12 @@ __device__ __forceinline__ float epilogue_op(float a, float bias, float gate, fl
 template <int ACT, int BN>
 __device__ __forceinline__ void store_row(const float (&acc)[BN], const Epilogue& ep, float* __restrict__ y, int ldy,
                                           int row, int n0, int Nout, bool vec_ok) {
-  const size_t ro = (size_t)row * ldy;
+  const size_t go = (size_t)row * ldy;                // gate offset (GEMM row)
+  size_t ro = go;                                     // output / residual offset
+  if (ep.transpose_n > 0) {
+    const long long n = ep.transpose_n, nn = n * n, b = row / nn, r = row % nn;
+    ro = (size_t)(b * nn + (r % n) * n + r / n) * ldy;
+  }
   const float sc = ep.row_scale ? __ldg(ep.row_scale + row) : 1.f;
 #pragma unroll
   for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -146,7 +153,7 @@ __device__ __forceinline__ void store_row(const float (&acc)[BN], const Epilogue
       float4 g[4], r[4];
       if (ACT == 2 || ACT == 4) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) g[u] = *reinterpret_cast<const float4*>(ep.gate + ro + col + 4 * u);
+        for (int u = 0; u < 4; ++u) g[u] = *reinterpret_cast<const float4*>(ep.gate + go + col + 4 * u);
       }
       if (ep.residual) {
 #pragma unroll
@@ -170,7 +177,7 @@ __device__ __forceinline__ void store_row(const float (&acc)[BN], const Epilogue
       for (int u = 0; u < 16; ++u) {
         if (col + u < Nout) {
           const float bv = ep.bias ? __ldg(ep.bias + col + u) : 0.f;
-          const float gg = (ACT == 2 || ACT == 4) ? ep.gate[ro + col + u] : 0.f;
+          const float gg = (ACT == 2 || ACT == 4) ? ep.gate[go + col + u] : 0.f;
           const float rr = ep.residual ? ep.residual[ro + col + u] : 0.f;
           y[ro + col + u] = epilogue_op<ACT>(acc[c0 + u], bv, gg, sc, rr);
         }
@@ -329,7 +336,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int ncol = min(BN, Nout - n0);
         if (ep.gate)
           for (int c = 0; c < ncol; c += 32) prefetch_l2(ep.gate + (size_t)row * ldy + n0 + c);
-        if (ep.residual)
+        if (ep.residual && ep.transpose_n == 0)
           for (int c = 0; c < ncol; c += 32) prefetch_l2(ep.residual + (size_t)row * ldy + n0 + c);
       }
       float acc[BN];
@@ -450,8 +457,8 @@ bool gemm_tf32x3_supported(int M, int Nout, int K, const float* x, int ldx, cons
 // act: see Epilogue.  tile_n: 0 = choose, else 32/64/128.
 int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                        const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
-                       float* y, int ldy, int tile_n) {
-  Epilogue ep{bias, residual, gate, row_scale, act};
+                       int transpose_n, float* y, int ldy, int tile_n) {
+  Epilogue ep{bias, residual, gate, row_scale, act, transpose_n};
   if (tile_n == 0) {
     // enough CTAs to cover the 148 SMs beats wide tiles for the small-M node GEMMs
     const int mt = ceil_div(M, kBM);
@@ -472,13 +479,15 @@ int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, i
 
 extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                                const float* bias, const float* residual, const float* gate, const float* row_scale,
-                               int act, float* y, int ldy, int tile_n) {
+                               int act, int transpose_n, float* y, int ldy, int tile_n) {
   ABX_REQUIRE(M > 0 && Nout > 0 && K > 0 && x && w && y, "abx_gemm_tf32x3: bad shape or null argument");
   ABX_REQUIRE(abx::gemm_tf32x3_supported(M, Nout, K, x, ldx, w, ldw),
               "abx_gemm_tf32x3: K, ldx, ldw must be multiples of 4 with ldx, ldw >= K, and x, w 16-byte aligned "
               "(K=%d ldx=%d ldw=%d)", K, ldx, ldw);
   ABX_REQUIRE(ldy >= Nout, "abx_gemm_tf32x3: ldy < Nout");
   ABX_REQUIRE(act >= 0 && act <= 4 && ((act != 2 && act != 4) || gate), "abx_gemm_tf32x3: bad activation / missing gate");
-  return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, residual, gate, row_scale, act, y,
-                                 ldy, tile_n);
+  ABX_REQUIRE(transpose_n >= 0 && (transpose_n == 0 || M % (transpose_n * transpose_n) == 0),
+              "abx_gemm_tf32x3: M must be a multiple of transpose_n^2");
+  return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, residual, gate, row_scale, act,
+                                 transpose_n, y, ldy, tile_n);
 }

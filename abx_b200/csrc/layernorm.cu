@@ -1,0 +1,85 @@
+// LayerNorm over the channel dimension of the pair / sequence activations (torch.nn.LayerNorm semantics,
+// eps inside the square root; reference: every `LayerNorm(...)` of abx/model/seqformer.py and
+// score_network.py:117-135).  One warp per row, the row held in registers (two-pass mean / variance),
+// 16-byte loads and stores: the kernel is a pure HBM stream (read C floats, write C floats per row).
+//
+// Optional output transposition of the two middle dimensions of a [B, n, n, C] tensor (row (b,i,j) is
+// written to (b,j,i)), which replaces the `rearrange(pair_act, 'b i j c -> b j i c')` copy in front of the
+// per-column triangle attention (seqformer.py:537-538).
+#include "common.cuh"
+
+namespace abx {
+
+constexpr int kLnWarps = 8, kLnMaxV = 8;   // up to 8 float4 per lane: C <= 1024
+
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
+    long long rows, int C, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float eps, int transpose_n, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = C >> 2;                        // float4 per row
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[kLnMaxV];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) {
+      v[k] = xr[i];
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  long long orow = row;
+  if (transpose_n > 0) {
+    const long long nn = (long long)transpose_n * transpose_n;
+    const long long b = row / nn, r = row % nn;
+    orow = b * nn + (r % transpose_n) * transpose_n + r / transpose_n;
+  }
+  float4* yr = reinterpret_cast<float4*>(y + orow * C);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int k = 0; k < kLnMaxV; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) {
+      const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+      float4 o;
+      o.x = (v[k].x - mean) * rstd * g.x + b.x;
+      o.y = (v[k].y - mean) * rstd * g.y + b.y;
+      o.z = (v[k].z - mean) * rstd * g.z + b.z;
+      o.w = (v[k].w - mean) * rstd * g.w + b.w;
+      yr[i] = o;
+    }
+  }
+}
+
+}  // namespace abx
+
+extern "C" int abx_layernorm(void* stream, long long rows, int C, const float* x, const float* gamma, const float* beta,
+                             float eps, int transpose_n, float* y) {
+  using namespace abx;
+  ABX_REQUIRE(rows > 0 && C > 0 && x && gamma && beta && y, "abx_layernorm: bad shape or null argument");
+  ABX_REQUIRE(C % 4 == 0 && C <= 32 * 4 * kLnMaxV, "abx_layernorm: C must be a multiple of 4 and <= %d (got %d)", 32 * 4 * kLnMaxV, C);
+  ABX_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0),
+              "abx_layernorm: pointers must be 16-byte aligned");
+  ABX_REQUIRE(transpose_n >= 0 && (transpose_n == 0 || rows % ((long long)transpose_n * transpose_n) == 0),
+              "abx_layernorm: rows must be a multiple of transpose_n^2");
+  ABX_REQUIRE(transpose_n == 0 || x != y, "abx_layernorm: the transposing form cannot run in place");
+  const long long blocks = (rows + kLnWarps - 1) / kLnWarps;
+  ABX_REQUIRE(blocks < 2147483647LL, "abx_layernorm: too many rows");
+  layernorm_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, (cudaStream_t)stream>>>(rows, C, x, gamma, beta, eps, transpose_n, y);
+  count_launch();
+  return check_launch("layernorm_kernel");
+}

@@ -41,7 +41,9 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _i, _vp, _vp]),
     'abx_igso3_build_tables': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'abx_linear_f32': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i]),
-    'abx_gemm_tf32x3': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i]),
+    'abx_gemm_tf32x3': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i]),
+    'abx_layernorm': (_i, [_vp, C.c_longlong, _i, _vp, _vp, _vp, C.c_float, _i, _vp]),
+    'abx_pair_attention': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     'abx_set_gemm_backend': (_i, [_i]),
     'abx_ipa_workspace_bytes': (_sz, [_i, _i]),
     'abx_ipa_pair_bias': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),

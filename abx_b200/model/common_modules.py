@@ -2,7 +2,6 @@
 import numpy as np
 import torch
 from torch import nn
-from torch.nn import LayerNorm  # noqa: F401  (re-exported, as the reference does)
 
 
 class ConfigView(dict):
@@ -33,22 +32,38 @@ def as_config(c):
     return c
 
 
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state_dict keys) on the streaming LayerNorm kernel (abx_layernorm).
+    `transpose_n=n` returns the result of a [B,n,n,C] input as 'b j i c'.  CUDA tensors only."""
+
+    def forward(self, x, transpose_n=0):
+        from abx_b200 import ops
+        C = x.shape[-1]
+        if C % 4 != 0 or C > 1024 or len(self.normalized_shape) != 1:
+            if not x.is_cuda:
+                raise ops.lib.AbxError('abx_b200 layers take CUDA tensors only (no CPU fallback)')
+            assert transpose_n == 0
+            return super().forward(x)
+        return ops.layer_norm(x, self.weight, self.bias, self.eps, transpose_n=transpose_n)
+
+
 class AbxLinear(nn.Linear):
     """nn.Linear (same parameters / state_dict keys) whose forward runs on the tcgen05 3xTF32 GEMM
     (abx_gemm_tf32x3) with the activation / gate / mask / residual of the surrounding reference code fused
     into the epilogue.  CUDA tensors only; layers whose input width is not a multiple of 4 (two small
     once-per-complex encoder layers) use torch's CUDA matmul."""
 
-    def forward(self, x, act=None, residual=None, gate=None, row_scale=None):
+    def forward(self, x, act=None, residual=None, gate=None, row_scale=None, transpose_n=0):
         from abx_b200 import ops
         if self.in_features % 4 != 0:
             if not x.is_cuda:
                 raise ops.lib.AbxError('abx_b200 layers take CUDA tensors only (no CPU fallback)')
-            assert act in (None, 'relu') and gate is None and row_scale is None
+            assert act in (None, 'relu') and gate is None and row_scale is None and transpose_n == 0
             y = torch.nn.functional.linear(x, self.weight, self.bias)
             y = torch.relu(y) if act == 'relu' else y
             return y if residual is None else y + residual
-        return ops.linear(x, self.weight, self.bias, act=act, residual=residual, gate=gate, row_scale=row_scale)
+        return ops.linear(x, self.weight, self.bias, act=act, residual=residual, gate=gate, row_scale=row_scale,
+                          transpose_n=transpose_n)
 
 
 def mlp(seq, x, residual=None):

@@ -70,13 +70,29 @@ class Attention(nn.Module):
             t = self.proj_in(q_data)
             t = t.reshape(t.shape[:-1] + (H, -1)).transpose(-2, -3)
             q, k, v = torch.chunk(t, 3, dim=-1)
+        # logits = (q / sqrt(d)) k^T + bias, keys masked to finfo.min, softmax, weights @ v  (seqformer.py:283-301).
+        # The key mask is folded into the (S-times smaller) bias once: min + q.k == min in fp32, exactly what
+        # masked_fill produces, and it keeps the big [B,S,H,L,L] tensor down to matmul / add_ / softmax_ / matmul.
         add = bias[:, None]                                                                           # b 1 h q k
-        neg = torch.finfo(q.dtype).min
-        add = add.masked_fill(~k_mask[:, :, None, None, :].bool(), neg) if k_mask is not None else add
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=add.expand(q.shape[:-1] + (k.shape[-2],)))
+        if k_mask is not None:
+            add = add.masked_fill(~k_mask[:, :, None, None, :].bool(), torch.finfo(q.dtype).min)
+        logits = torch.matmul(q * (q.shape[-1] ** -0.5), k.transpose(-1, -2))
+        logits += add
+        o = torch.matmul(torch.softmax(logits, dim=-1), v)
         o = o.transpose(-2, -3).reshape(q_data.shape[:-1] + (-1,))
         gated = self.gate(q_data, act='sigmoid_mul', gate=o)                  # sigmoid(gate(q)) * o in the epilogue
         return self.proj_out(gated, residual=residual)
+
+
+    def forward_pair(self, x, bias, key_mask, residual=None, transpose_n=0):
+        """Self-attention over the rows of a [B,S,L,C] pair tensor on the fused kernels: one q|k|v GEMM, the
+        attention core without materialised logits (abx_pair_attention), gate and residual in GEMM epilogues.
+        `transpose_n`: x is the 'b j i c' view of the pair tensor; output / residual are 'b i j c'."""
+        from abx_b200 import ops
+        qkv = ops.linear(x, self._qkv_weight())
+        o = ops.pair_attention(qkv, bias, key_mask, self.num_head)
+        gated = self.gate(x, act='sigmoid_mul', gate=o)
+        return self.proj_out(gated, residual=residual, transpose_n=transpose_n)
 
 
 class SeqAttentionWithPairBias(nn.Module):
@@ -171,16 +187,12 @@ class TriangleAttention(nn.Module):
         self.config = c
 
     def forward(self, pair_act, seq_mask, residual=None):
-        """seqformer.py:506-550 (+ residual, fused for the per-row orientation)."""
-        if self.per_column:
-            x = self.norm(pair_act).transpose(1, 2).contiguous()
-        else:
-            x = self.norm(pair_act)
+        """seqformer.py:506-550 (+ residual).  Per-column orientation: the LayerNorm kernel writes its output
+        transposed ('b j i c') and the output projection stores back transposed, so no rearrange copies."""
+        n = pair_act.shape[1] if self.per_column else 0
+        x = self.norm(pair_act, transpose_n=n)
         bias = self.proj_pair(x).permute(0, 3, 1, 2)
-        if self.per_column:
-            out = self.attn(x, x, bias=bias, k_mask=seq_mask[:, None, :]).transpose(1, 2)
-            return out if residual is None else residual + out
-        return self.attn(x, x, bias=bias, k_mask=seq_mask[:, None, :], residual=residual)
+        return self.attn.forward_pair(x, bias, seq_mask, residual=residual, transpose_n=n)
 
 
 class SeqformerIteration(nn.Module):

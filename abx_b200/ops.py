@@ -10,11 +10,12 @@ from abx_b200 import lib
 ACT = {None: 0, 'none': 0, 'relu': 1, 'gate': 2, 'sigmoid': 3, 'sigmoid_mul': 4}
 
 
-def linear(x, weight, bias=None, act=None, residual=None, gate=None, row_scale=None, out=None, tile_n=0):
+def linear(x, weight, bias=None, act=None, residual=None, gate=None, row_scale=None, out=None, tile_n=0, transpose_n=0):
     """x [..., K] (last dim contiguous, uniform row stride), weight [Nout, K] -> [..., Nout].
 
     v = xW^T + b;  act: None | 'relu' | 'sigmoid' | 'gate' (v * sigmoid(gate)) | 'sigmoid_mul' (sigmoid(v) * gate)
-    with gate [..., Nout];  then y = v * row_scale[...] + residual[..., Nout]."""
+    with gate [..., Nout];  then y = v * row_scale[...] + residual[..., Nout].
+    transpose_n = n: x is [B,n,n,K] and the result (and residual) are indexed 'b j i c' (see the header)."""
     L = lib.load()
     K = x.shape[-1]
     Nout = weight.shape[0]
@@ -36,10 +37,41 @@ def linear(x, weight, bias=None, act=None, residual=None, gate=None, row_scale=N
     with lib.device_guard(x2):
         lib.check(L.abx_gemm_tf32x3(lib.stream(), M, Nout, K, lib.ptr_any(x2), ldx, lib.ptr(w, torch.float32), K,
                                     lib.ptr(bias.detach() if bias is not None else None), lib.ptr(res), lib.ptr(g),
-                                    lib.ptr(rs), ACT[act], lib.ptr(y), Nout, tile_n))
+                                    lib.ptr(rs), ACT[act], transpose_n, lib.ptr(y), Nout, tile_n))
     return y
 
 
 def set_gemm_backend(name):
     """'auto' | 'simt' | 'tcgen05' for the node GEMMs inside abx_ipa_forward."""
     lib.check(lib.load().abx_set_gemm_backend({'auto': 0, 'simt': 1, 'tcgen05': 2}[name]))
+
+
+def layer_norm(x, weight, bias, eps=1e-5, transpose_n=0):
+    """torch.nn.functional.layer_norm over the last dimension on the streaming LayerNorm kernel.
+    transpose_n = n: x is [B,n,n,C] and the result is returned as 'b j i c' (contiguous)."""
+    L = lib.load()
+    C = x.shape[-1]
+    xc = x if (x.is_contiguous() and x.dtype == torch.float32) else x.float().contiguous()
+    y = torch.empty_like(xc)
+    with lib.device_guard(xc):
+        lib.check(L.abx_layernorm(lib.stream(), xc.numel() // C, C, lib.ptr(xc), lib.ptr(weight.detach(), torch.float32),
+                                  lib.ptr(bias.detach(), torch.float32), float(eps), transpose_n, lib.ptr(y)))
+    return y
+
+
+def pair_attention(qkv, bias, key_mask, num_head):
+    """Fused attention core for TriangleAttention.  qkv [B,S,L,3*H*D] (q | k | v slices of one projection),
+    bias [B,H,L,L], key_mask [B,L] (bool/float, None = keep all)  ->  [B,S,L,H*D]."""
+    L_ = lib.load()
+    B, S, L, C3 = qkv.shape
+    HD = C3 // 3
+    D = HD // num_head
+    assert qkv.is_contiguous() and qkv.dtype == torch.float32
+    bias = bias.float().contiguous()
+    km = key_mask.to(torch.float32).contiguous() if key_mask is not None else None
+    out = torch.empty(B, S, L, HD, device=qkv.device, dtype=torch.float32)
+    base, esz = qkv.data_ptr(), 4
+    with lib.device_guard(qkv):
+        lib.check(L_.abx_pair_attention(lib.stream(), B, S, L, num_head, D, base, base + HD * esz, base + 2 * HD * esz, C3,
+                                        lib.ptr(bias), lib.ptr(km), lib.ptr(out)))
+    return out

@@ -121,11 +121,32 @@ int abx_linear_f32(void* stream, int M, int Nout, int K, const float* x, int ldx
  *   v = acc + bias;  act: 0 none, 1 relu(v), 2 v * sigmoid(gate), 3 sigmoid(v), 4 sigmoid(v) * gate
  *   (gate [M,ldy]);  then y = v * row_scale[row] + residual   (row_scale [M], residual [M,ldy]; all optional)
  *   — the gated projections, masked projections and residual adds of seqformer.py fused into the GEMM
+ *   transpose_n = n > 0: the M rows are (b,i,j) of a [B,n,n,*] tensor and row (b,i,j) of the result is stored
+ *   at (b,j,i) (y and residual are indexed by the transposed row; gate / row_scale by the GEMM row) — the
+ *   'b i j c -> b j i c' rearrange after the per-column triangle attention (seqformer.py:547-548)
  *   requirements: K, ldx, ldw multiples of 4; x, w 16-byte aligned
  *   tile_n: output tile width 32/64/128, 0 = chosen from the problem shape */
 int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                     const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
-                    float* y, int ldy, int tile_n);
+                    int transpose_n, float* y, int ldy, int tile_n);
+
+/* ---- LayerNorm ------------------------------------------------------------------------------- */
+/* y = (x - mean) / sqrt(var + eps) * gamma + beta over the last dimension (torch.nn.LayerNorm; every
+ * LayerNorm of abx/model/seqformer.py, score_network.py:117-135).  x, y [rows, C] contiguous, C % 4 == 0,
+ * C <= 1024.  transpose_n = n > 0: row (b,i,j) of a [B,n,n,C] input is written to (b,j,i) (the rearrange in
+ * front of the per-column triangle attention, seqformer.py:537-538); not in place. */
+int abx_layernorm(void* stream, long long rows, int C, const float* x, const float* gamma, const float* beta,
+                  float eps, int transpose_n, float* y);
+
+/* ---- attention with pair bias ------------------------------------------------------------------ */
+/* Attention core of seqformer.py:283-301 for TriangleAttention (:506-550), logits never materialised:
+ *   out[b,s,i,h,:] = sum_j softmax_j(q[b,s,i,h,:].k[b,s,j,h,:]/sqrt(D) + bias[b,h,i,j]) v[b,s,j,h,:]
+ * with keys whose key_mask[b,j] == 0 set to finfo.min before the softmax.
+ *   q, k, v: element (b,s,l,h,d) at ptr[((b*S+s)*L + l)*ld + h*D + d]  (e.g. three slices of one fused
+ *   q|k|v projection buffer, ld = 3*H*D);  bias [B,H,L,L];  key_mask [B,L] f32 or NULL;  out [B,S,L,H*D]
+ *   D in {16,32,48,64}; 2*L*D*4 bytes of K/V must fit in shared memory (L <= ~520 at D = 48). */
+int abx_pair_attention(void* stream, int B, int S, int L, int H, int D, const float* q, const float* k,
+                       const float* v, int ld, const float* bias, const float* key_mask, float* out);
 
 /* Which GEMM the IPA pipeline uses for its node layers: 0 auto (tcgen05 when operands qualify),
  * 1 SIMT (abx_linear_f32), 2 tcgen05 only.  Process-wide; meant for A/B measurements and tests. */

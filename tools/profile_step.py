@@ -49,10 +49,10 @@ def main():
         orig = ops.linear
         recs = []
 
-        def timed_linear(x, weight, bias=None, act=None, residual=None, gate=None, row_scale=None, out=None, tile_n=0):
+        def timed_linear(x, weight, bias=None, act=None, residual=None, gate=None, **kw):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            y = orig(x, weight, bias, act, residual, gate, row_scale, out, tile_n)
+            y = orig(x, weight, bias, act, residual, gate, **kw)
             e1.record()
             M = x.numel() // x.shape[-1]
             recs.append(((M, weight.shape[0], x.shape[-1], act, residual is not None, gate is not None, x.is_contiguous()), e0, e1))
