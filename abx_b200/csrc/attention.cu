@@ -46,17 +46,20 @@ __global__ void __launch_bounds__(kAttMaxThreads, 1) pair_attention_kernel(
   const int i = wrow0 + lane;                      // query row of this lane
   const bool row_ok = i < L;
   const int ic = row_ok ? i : L - 1;
-  float qr[D], acc[D];
+  // packed fp32 pairs: the inner products and the value accumulation run on FFMA2 (fma.rn.f32x2, sm_100),
+  // two FMAs per issued instruction
+  float2 qr[D / 2], acc[D / 2];
   {
     const float4* qp = reinterpret_cast<const float4*>(q + (row0 + ic) * (size_t)ld + h * D);
 #pragma unroll
     for (int d4 = 0; d4 < D4; ++d4) {
       const float4 t = __ldg(qp + d4);
-      qr[4 * d4] = t.x * scale; qr[4 * d4 + 1] = t.y * scale; qr[4 * d4 + 2] = t.z * scale; qr[4 * d4 + 3] = t.w * scale;
+      qr[2 * d4] = make_float2(t.x * scale, t.y * scale);
+      qr[2 * d4 + 1] = make_float2(t.z * scale, t.w * scale);
     }
   }
 #pragma unroll
-  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  for (int d = 0; d < D / 2; ++d) acc[d] = make_float2(0.f, 0.f);
   float m = -FLT_MAX, l = 0.f;
   float* bt = Bt + warp * (32 * 33);
   const float* bias_bh = bias + ((size_t)b * H + h) * L * L;
@@ -77,14 +80,14 @@ __global__ void __launch_bounds__(kAttMaxThreads, 1) pair_attention_kernel(
     for (int jj = 0; jj < kAttChunk; ++jj) {
       if (jj < nj) {
         const float4* kr = reinterpret_cast<const float4*>(Ks + (size_t)(j0 + jj) * D);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        float2 da = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
 #pragma unroll
         for (int d4 = 0; d4 < D4; ++d4) {
           const float4 kk = kr[d4];
-          d0 = fmaf(qr[4 * d4], kk.x, d0); d1 = fmaf(qr[4 * d4 + 1], kk.y, d1);
-          d2 = fmaf(qr[4 * d4 + 2], kk.z, d2); d3 = fmaf(qr[4 * d4 + 3], kk.w, d3);
+          da = __ffma2_rn(qr[2 * d4], make_float2(kk.x, kk.y), da);
+          db = __ffma2_rn(qr[2 * d4 + 1], make_float2(kk.z, kk.w), db);
         }
-        float sv = ((d0 + d1) + (d2 + d3)) + bt[lane * 33 + jj];
+        float sv = ((da.x + da.y) + (db.x + db.y)) + bt[lane * 33 + jj];
         sv = (Ms[j0 + jj] != 0.f) ? sv : -FLT_MAX;                    // masked_fill(~k_mask, finfo.min)
         s[jj] = sv;
         cmax = fmaxf(cmax, sv);
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(kAttMaxThreads, 1) pair_attention_kernel(
     const float corr = expf(m - m_new);
     l *= corr;
 #pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] *= corr;
+    for (int d = 0; d < D / 2; ++d) { acc[d].x *= corr; acc[d].y *= corr; }
     m = m_new;
 #pragma unroll
     for (int jj = 0; jj < kAttChunk; ++jj) {
@@ -105,10 +108,12 @@ __global__ void __launch_bounds__(kAttMaxThreads, 1) pair_attention_kernel(
         l += p;
         const float4* vr = reinterpret_cast<const float4*>(Vs + (size_t)(j0 + jj) * D);
 #pragma unroll
+        const float2 pp = make_float2(p, p);
+#pragma unroll
         for (int d4 = 0; d4 < D4; ++d4) {
           const float4 vv = vr[d4];
-          acc[4 * d4] = fmaf(p, vv.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(p, vv.y, acc[4 * d4 + 1]);
-          acc[4 * d4 + 2] = fmaf(p, vv.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(p, vv.w, acc[4 * d4 + 3]);
+          acc[2 * d4] = __ffma2_rn(pp, make_float2(vv.x, vv.y), acc[2 * d4]);
+          acc[2 * d4 + 1] = __ffma2_rn(pp, make_float2(vv.z, vv.w), acc[2 * d4 + 1]);
         }
       }
     }
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(kAttMaxThreads, 1) pair_attention_kernel(
     float4* op = reinterpret_cast<float4*>(out + (row0 + i) * (size_t)(H * D) + h * D);
 #pragma unroll
     for (int d4 = 0; d4 < D4; ++d4)
-      op[d4] = make_float4(acc[4 * d4] * inv, acc[4 * d4 + 1] * inv, acc[4 * d4 + 2] * inv, acc[4 * d4 + 3] * inv);
+      op[d4] = make_float4(acc[2 * d4].x * inv, acc[2 * d4].y * inv, acc[2 * d4 + 1].x * inv, acc[2 * d4 + 1].y * inv);
   }
 }
 

@@ -134,11 +134,28 @@ __global__ void __launch_bounds__(256) ipa_pair_bias_kernel(int N, const float* 
 // stride odd -> conflict-free with lanes on rows), so the softmax is the exact two-pass one.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kRows = 32, kAttnThreads = 256, kAttnWarps = kAttnThreads / 32, kOld = kVD + 1;
+constexpr int kKeyChunk = 8;                        // keys per cp.async stage of a warp
+constexpr int kStageFloats = kKeyChunk * kVD;       // one stage holds 8 key rows (28 floats) or 8 value rows (40)
 
 __host__ __device__ inline int attn_ld(int N) { return N | 1; }
-__host__ inline size_t attn_smem_bytes(int N) {
+__host__ __device__ inline size_t attn_tile_floats(int N) {
   size_t a = (size_t)kRows * attn_ld(N), b = (size_t)kAttnWarps * kRows * kOld;
-  return (a > b ? a : b) * sizeof(float);
+  return ((a > b ? a : b) + 3) & ~(size_t)3;        // keep the staging area 16-byte aligned
+}
+__host__ inline size_t attn_smem_bytes(int N) {
+  return (attn_tile_floats(N) + (size_t)kAttnWarps * 2 * kStageFloats) * sizeof(float);
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Stage `nkeys` consecutive rows of `row_floats` floats (a multiple of 4) from global into a warp-private buffer.
+__device__ __forceinline__ void stage_rows(float* dst, const float* src, int nkeys, int row_floats, int lane) {
+  const int n4 = nkeys * row_floats / 4;
+  for (int i = lane; i < n4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
 }
 
 __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
@@ -162,7 +179,11 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
   }
   __syncthreads();
 
-  // 2. logits: lane = query row, warps stride over keys (key operands are warp-uniform loads)
+  // 2. logits: lane = query row; each warp owns a contiguous range of keys and streams their packed rows
+  //    through a warp-private double buffer with cp.async, so the key operands are shared-memory broadcasts
+  const int per_warp = (N + kAttnWarps - 1) / kAttnWarps;
+  const int jb = min(N, wid * per_warp), je = min(N, jb + per_warp);
+  float* stage = S + attn_tile_floats(N) + (size_t)wid * 2 * kStageFloats;
   {
     const int i = i0 + lane;
     const bool row_ok = i < N;
@@ -179,22 +200,39 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
     const float gamma = (pw > 20.f) ? pw : log1pf(expf(pw));                    // F.softplus  folding.py:96
     const float coef = -0.5f * sqrtf(1.0f / (3.0f * kPqk * 9.0f / 2.0f)) * gamma;   // -1/2 w_point gamma  :97-99
     const float mi = row_ok ? __ldg(mask + (size_t)b * N + i) : 0.f;
-    const float4* Kbh = reinterpret_cast<const float4*>(Kdat + bh * N * kQK);
-    for (int j = wid; j < N; j += kAttnWarps) {
-      float k[kQK];
+    const float* Kbh = Kdat + bh * N * kQK;
+    if (jb < je) stage_rows(stage, Kbh + (size_t)jb * kQK, min(kKeyChunk, je - jb), kQK, lane);
+    cp_async_commit();
+    int buf = 0;
+    for (int jc = jb; jc < je; jc += kKeyChunk, buf ^= 1) {
+      const int nk = min(kKeyChunk, je - jc);
+      if (jc + kKeyChunk < je)
+        stage_rows(stage + (buf ^ 1) * kStageFloats, Kbh + (size_t)(jc + kKeyChunk) * kQK, min(kKeyChunk, je - jc - kKeyChunk), kQK, lane);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      const float* kbuf = stage + buf * kStageFloats;
+#pragma unroll 2
+      for (int t = 0; t < nk; ++t) {
+        const int j = jc + t;
+        const float4* kp = reinterpret_cast<const float4*>(kbuf + t * kQK);
+        float k[kQK];
 #pragma unroll
-      for (int u = 0; u < kQK / 4; ++u) { float4 v = __ldg(Kbh + (size_t)j * (kQK / 4) + u); k[4 * u] = v.x; k[4 * u + 1] = v.y; k[4 * u + 2] = v.z; k[4 * u + 3] = v.w; }
-      float dot = 0.f, d2 = 0.f;
+        for (int u = 0; u < kQK / 4; ++u) { float4 v = kp[u]; k[4 * u] = v.x; k[4 * u + 1] = v.y; k[4 * u + 2] = v.z; k[4 * u + 3] = v.w; }
+        float dot = 0.f, d2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < kSqk; ++c) dot = fmaf(q[c], k[c], dot);
+        for (int c = 0; c < kSqk; ++c) dot = fmaf(q[c], k[c], dot);
 #pragma unroll
-      for (int c = kSqk; c < kQK; ++c) { float d = q[c] - k[c]; d2 = fmaf(d, d, d2); }
-      if (row_ok) {
-        float lg = (dot + coef * d2) + S[lane * ld + j];
-        bool ok = (mi * __ldg(mask + (size_t)b * N + j)) != 0.f;                // mask_2d  folding.py:106-109
-        S[lane * ld + j] = ok ? lg : -FLT_MAX;
+        for (int c = kSqk; c < kQK; ++c) { float d = q[c] - k[c]; d2 = fmaf(d, d, d2); }
+        if (row_ok) {
+          float lg = (dot + coef * d2) + S[lane * ld + j];
+          bool ok = (mi * __ldg(mask + (size_t)b * N + j)) != 0.f;                // mask_2d  folding.py:106-109
+          S[lane * ld + j] = ok ? lg : -FLT_MAX;
+        }
       }
+      __syncwarp();                                  // the buffer being refilled next round is no longer read
     }
+    cp_async_wait<0>();
   }
   __syncthreads();
 
@@ -214,21 +252,38 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
   }
   __syncthreads();
 
-  // 4. scalar + point values: lane = row, warps split the keys, then an 8-way reduction through smem
+  // 4. scalar + point values: lane = row, each warp accumulates over its key range (value rows streamed like
+  //    the key rows), then an 8-way reduction through smem
   {
     float acc[kVD];
 #pragma unroll
     for (int d = 0; d < kVD; ++d) acc[d] = 0.f;
-    const float4* Vbh = reinterpret_cast<const float4*>(Vdat + bh * N * kVD);
-    for (int j = wid; j < N; j += kAttnWarps) {
-      const float s = S[lane * ld + j];
+    const float* Vbh = Vdat + bh * N * kVD;
+    if (jb < je) stage_rows(stage, Vbh + (size_t)jb * kVD, min(kKeyChunk, je - jb), kVD, lane);
+    cp_async_commit();
+    int buf = 0;
+    for (int jc = jb; jc < je; jc += kKeyChunk, buf ^= 1) {
+      const int nk = min(kKeyChunk, je - jc);
+      if (jc + kKeyChunk < je)
+        stage_rows(stage + (buf ^ 1) * kStageFloats, Vbh + (size_t)(jc + kKeyChunk) * kVD, min(kKeyChunk, je - jc - kKeyChunk), kVD, lane);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      const float* vbuf = stage + buf * kStageFloats;
+#pragma unroll 2
+      for (int t = 0; t < nk; ++t) {
+        const float sv = S[lane * ld + jc + t];
+        const float4* vp = reinterpret_cast<const float4*>(vbuf + t * kVD);
 #pragma unroll
-      for (int u = 0; u < kVD / 4; ++u) {
-        float4 v = __ldg(Vbh + (size_t)j * (kVD / 4) + u);
-        acc[4 * u] = fmaf(s, v.x, acc[4 * u]); acc[4 * u + 1] = fmaf(s, v.y, acc[4 * u + 1]);
-        acc[4 * u + 2] = fmaf(s, v.z, acc[4 * u + 2]); acc[4 * u + 3] = fmaf(s, v.w, acc[4 * u + 3]);
+        for (int u = 0; u < kVD / 4; ++u) {
+          const float4 v = vp[u];
+          acc[4 * u] = fmaf(sv, v.x, acc[4 * u]); acc[4 * u + 1] = fmaf(sv, v.y, acc[4 * u + 1]);
+          acc[4 * u + 2] = fmaf(sv, v.z, acc[4 * u + 2]); acc[4 * u + 3] = fmaf(sv, v.w, acc[4 * u + 3]);
+        }
       }
+      __syncwarp();
     }
+    cp_async_wait<0>();
     __syncthreads();                       // everyone is done reading S; reuse it for the partial sums
     float* P = S + (size_t)(wid * kRows + lane) * kOld;
 #pragma unroll
@@ -280,7 +335,7 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
 // every 4th z[i,j,:] row straight from HBM into registers (one 16-byte load per lane covers the 512 B
 // row), 48 FMAs per load; the four partial sums are reduced through shared memory.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kAggThreads = 128, kAggWarps = kAggThreads / 32, kAggUnroll = 4;
+constexpr int kAggThreads = 128, kAggWarps = kAggThreads / 32, kAggUnroll = 8;
 
 __global__ void __launch_bounds__(kAggThreads) ipa_pair_aggregate_kernel(int N, const float* __restrict__ z,
                                                                          const float* __restrict__ probs,
@@ -376,11 +431,16 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
                         float* feats, const IpaWorkspace& ws) {
   const int M = B * N;
   int rc;
-  // node projections (folding.py:69-86): four Linear layers into one [M, 1152] buffer
+  // node projections (folding.py:69-86): four Linear layers into one [M, 1152] buffer — one GEMM when the
+  // caller provides the row-concatenated weights
+  if (w->w_proj_cat) {
+    if ((rc = launch_linear_f32(s, M, kProj, kC, x, kC, w->w_proj_cat, w->b_proj_cat, nullptr, 0, ws.proj, kProj))) return rc;
+  } else {
   if ((rc = launch_linear_f32(s, M, kH * kSqk, kC, x, kC, w->w_q_scalar, w->b_q_scalar, nullptr, 0, ws.proj, kProj))) return rc;
   if ((rc = launch_linear_f32(s, M, kH * (kSqk + kSv), kC, x, kC, w->w_kv_scalar, w->b_kv_scalar, nullptr, 0, ws.proj + kOffKV, kProj))) return rc;
   if ((rc = launch_linear_f32(s, M, 3 * kH * kPqk, kC, x, kC, w->w_q_point, w->b_q_point, nullptr, 0, ws.proj + kOffQP, kProj))) return rc;
   if ((rc = launch_linear_f32(s, M, 3 * kH * (kPqk + kPv), kC, x, kC, w->w_kv_point, w->b_kv_point, nullptr, 0, ws.proj + kOffKVP, kProj))) return rc;
+  }
   ipa_pack_kernel<<<ceil_div(M * kH, 128), 128, 0, s>>>(B, N, ws.proj, rots, trans, ws.Qdat, ws.Kdat, ws.Vdat);
   count_launch();
   if ((rc = check_launch("ipa_pack_kernel"))) return rc;

@@ -23,7 +23,8 @@ class DiffuserConsts(C.Structure):
 class IpaWeights(C.Structure):
     """abx_ipa_weights (include/abx_b200.h)."""
     _fields_ = [(n, _vp) for n in ('w_q_scalar', 'b_q_scalar', 'w_kv_scalar', 'b_kv_scalar', 'w_q_point', 'b_q_point',
-                                   'w_kv_point', 'b_kv_point', 'w_pair', 'b_pair', 'point_weights', 'w_final', 'b_final')]
+                                   'w_kv_point', 'b_kv_point', 'w_pair', 'b_pair', 'point_weights', 'w_final', 'b_final',
+                                   'w_proj_cat', 'b_proj_cat')]
 
 
 # name -> (restype, argtypes); mirrors include/abx_b200.h one to one (tests/test_abi.py cross-checks the header)

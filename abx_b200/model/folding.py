@@ -58,9 +58,13 @@ class InvariantPointAttention(nn.Module):
               self.proj_q_point_local.weight, self.proj_q_point_local.bias, self.proj_kv_point_local.weight,
               self.proj_kv_point_local.bias, self.proj_pair.weight, self.proj_pair.bias, self.trainable_point_weights,
               self.final_proj.weight, self.final_proj.bias]
-        key = tuple(p.data_ptr() for p in ps)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
         if self._wstruct is None or self._wstruct[0] != key:
-            self._wstruct = (key, lib.IpaWeights(*(lib.ptr(p.detach(), torch.float32) for p in ps)))
+            with torch.no_grad():        # the four projections as one [1152, C] operand (one GEMM per layer-call)
+                wcat = torch.cat([ps[0], ps[2], ps[4], ps[6]], dim=0).float().contiguous()
+                bcat = torch.cat([ps[1], ps[3], ps[5], ps[7]], dim=0).float().contiguous()
+            self._wstruct = (key, lib.IpaWeights(*(lib.ptr(p.detach(), torch.float32) for p in ps), lib.ptr(wcat), lib.ptr(bcat)),
+                             (wcat, bcat))
         return self._wstruct[1]
 
     def pair_bias(self, inputs_2d):

@@ -163,6 +163,9 @@ typedef struct {
   const float* w_pair;      const float* b_pair;        /* [H, Cz], [H]             proj_pair           */
   const float* point_weights;                           /* [H]                      trainable_point_weights */
   const float* w_final;     const float* b_final;       /* [C, H*(16+8*4+Cz)], [C]  final_proj          */
+  /* optional: the four projection weights / biases concatenated by rows in the order above
+   * ([H*16 + H*32 + 3*H*4 + 3*H*12 = 1152, C] and [1152]) so that they run as one GEMM; NULL = four GEMMs */
+  const float* w_proj_cat;  const float* b_proj_cat;
 } abx_ipa_weights;
 
 /* Geometry of the supported configuration (config/config_model.json:107-124): H=12 heads, 16 scalar

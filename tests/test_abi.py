@@ -41,7 +41,7 @@ def test_ctypes_signatures_mirror_the_header():
 def test_struct_layouts():
     from abx_b200 import lib
     assert ctypes.sizeof(lib.DiffuserConsts) == 7 * 8 + 2 * 4
-    assert ctypes.sizeof(lib.IpaWeights) == 13 * 8
+    assert ctypes.sizeof(lib.IpaWeights) == 15 * 8
 
 
 def test_errors_are_reported_not_thrown():
