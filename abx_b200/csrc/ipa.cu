@@ -219,11 +219,15 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
         float k[kQK];
 #pragma unroll
         for (int u = 0; u < kQK / 4; ++u) { float4 v = kp[u]; k[4 * u] = v.x; k[4 * u + 1] = v.y; k[4 * u + 2] = v.z; k[4 * u + 3] = v.w; }
-        float dot = 0.f, d2 = 0.f;
+        float2 dot2 = make_float2(0.f, 0.f), dd2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < kSqk; ++c) dot = fmaf(q[c], k[c], dot);
+        for (int c = 0; c < kSqk; c += 2) dot2 = __ffma2_rn(make_float2(q[c], q[c + 1]), make_float2(k[c], k[c + 1]), dot2);
 #pragma unroll
-        for (int c = kSqk; c < kQK; ++c) { float d = q[c] - k[c]; d2 = fmaf(d, d, d2); }
+        for (int c = kSqk; c < kQK; c += 2) {
+          const float2 d = make_float2(q[c] - k[c], q[c + 1] - k[c + 1]);
+          dd2 = __ffma2_rn(d, d, dd2);
+        }
+        const float dot = dot2.x + dot2.y, d2 = dd2.x + dd2.y;
         if (row_ok) {
           float lg = (dot + coef * d2) + S[lane * ld + j];
           bool ok = (mi * __ldg(mask + (size_t)b * N + j)) != 0.f;                // mask_2d  folding.py:106-109
@@ -255,9 +259,9 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
   // 4. scalar + point values: lane = row, each warp accumulates over its key range (value rows streamed like
   //    the key rows), then an 8-way reduction through smem
   {
-    float acc[kVD];
+    float2 acc[kVD / 2];
 #pragma unroll
-    for (int d = 0; d < kVD; ++d) acc[d] = 0.f;
+    for (int d = 0; d < kVD / 2; ++d) acc[d] = make_float2(0.f, 0.f);
     const float* Vbh = Vdat + bh * N * kVD;
     if (jb < je) stage_rows(stage, Vbh + (size_t)jb * kVD, min(kKeyChunk, je - jb), kVD, lane);
     cp_async_commit();
@@ -277,8 +281,8 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
 #pragma unroll
         for (int u = 0; u < kVD / 4; ++u) {
           const float4 v = vp[u];
-          acc[4 * u] = fmaf(sv, v.x, acc[4 * u]); acc[4 * u + 1] = fmaf(sv, v.y, acc[4 * u + 1]);
-          acc[4 * u + 2] = fmaf(sv, v.z, acc[4 * u + 2]); acc[4 * u + 3] = fmaf(sv, v.w, acc[4 * u + 3]);
+          acc[2 * u] = __ffma2_rn(make_float2(sv, sv), make_float2(v.x, v.y), acc[2 * u]);
+          acc[2 * u + 1] = __ffma2_rn(make_float2(sv, sv), make_float2(v.z, v.w), acc[2 * u + 1]);
         }
       }
       __syncwarp();
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
     __syncthreads();                       // everyone is done reading S; reuse it for the partial sums
     float* P = S + (size_t)(wid * kRows + lane) * kOld;
 #pragma unroll
-    for (int d = 0; d < kVD; ++d) P[d] = acc[d];
+    for (int d = 0; d < kVD / 2; ++d) { P[2 * d] = acc[d].x; P[2 * d + 1] = acc[d].y; }
   }
   __syncthreads();
   for (int o = threadIdx.x; o < kRows * kVD; o += kAttnThreads) {
@@ -349,9 +353,10 @@ __global__ void __launch_bounds__(kAggThreads) ipa_pair_aggregate_kernel(int N, 
   }
   __syncthreads();
 
-  float acc[kH][4];
+  // packed fp32 pairs: 24 FFMA2 (fma.rn.f32x2) instead of 48 FFMA per 16-byte z load
+  float2 acc[kH][2];
 #pragma unroll
-  for (int h = 0; h < kH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+  for (int h = 0; h < kH; ++h) acc[h][0] = acc[h][1] = make_float2(0.f, 0.f);
   const float4* zrow = reinterpret_cast<const float4*>(z + ((size_t)b * N + i) * N * kCz) + lane;
   for (int j0 = wid; j0 < N; j0 += kAggWarps * kAggUnroll) {
     float4 zv[kAggUnroll];
@@ -368,10 +373,12 @@ __global__ void __launch_bounds__(kAggThreads) ipa_pair_aggregate_kernel(int N, 
         float a[kH];
 #pragma unroll
         for (int k = 0; k < kH / 4; ++k) { float4 v = ap[k]; a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w; }
+        const float2 zlo = make_float2(zv[u].x, zv[u].y), zhi = make_float2(zv[u].z, zv[u].w);
 #pragma unroll
         for (int h = 0; h < kH; ++h) {
-          acc[h][0] = fmaf(a[h], zv[u].x, acc[h][0]); acc[h][1] = fmaf(a[h], zv[u].y, acc[h][1]);
-          acc[h][2] = fmaf(a[h], zv[u].z, acc[h][2]); acc[h][3] = fmaf(a[h], zv[u].w, acc[h][3]);
+          const float2 aa = make_float2(a[h], a[h]);
+          acc[h][0] = __ffma2_rn(aa, zlo, acc[h][0]);
+          acc[h][1] = __ffma2_rn(aa, zhi, acc[h][1]);
         }
       }
     }
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(kAggThreads) ipa_pair_aggregate_kernel(int N, 
   float4* red = reinterpret_cast<float4*>(A);
 #pragma unroll
   for (int h = 0; h < kH; ++h)
-    red[(wid * kH + h) * (kCz / 4) + lane] = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+    red[(wid * kH + h) * (kCz / 4) + lane] = make_float4(acc[h][0].x, acc[h][0].y, acc[h][1].x, acc[h][1].y);
   __syncthreads();
   float4* out = reinterpret_cast<float4*>(feats + ((size_t)b * N + i) * kFeat + kFeatPair);   // 'b i h c -> b i (h c)'
   for (int o = threadIdx.x; o < kH * kCz / 4; o += kAggThreads) {

@@ -46,10 +46,66 @@ def _frame_output(batch, model_out, seq_t, diffuse_mask, antibody_len, t, to_hos
     return {'seq': seq, 'atom14_results': atom14, 'pLDDT': plddt, 'time': t}
 
 
+STATE_KEYS = ('rigids_t', 'seq_t', 'prev_pos', 'prev_seq', 'prev_pair')
+
+
+class GraphedReverseStep:
+    """One reverse iteration (model forward = 3 trunk passes, get_prev, SE(3)/categorical reverse step) captured
+    in a CUDA graph and replayed for every t of the loop: ~1100 kernel launches per iteration become one graph
+    launch, so the host never gates the GPU.  The iteration reads and writes five state tensors
+    (STATE_KEYS) plus the scalar t; they live in static buffers that the graph's outputs are copied back into."""
+
+    def __init__(self, batch, step_fn, generator=None):
+        dev = batch['rigids_t'].device
+        self.batch = batch
+        batch['rigids_t'] = batch['rigids_t'].to(torch.float64).contiguous()     # exact widening; reverse() returns float64
+        batch['seq_t'] = batch['seq_t'].long().contiguous()
+        self.state = {k: batch[k] for k in STATE_KEYS}
+        self.t = torch.ones(batch['rigids_t'].shape[0], device=dev, dtype=torch.float64)
+        snapshot = {k: v.clone() for k, v in self.state.items()}
+        rng = generator.get_state() if generator is not None else torch.cuda.get_rng_state(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # eager run: lazy initialisations happen outside the capture
+            step_fn(batch, self.t)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self._restore(snapshot)
+        if generator is not None:                          # the warm-up must not shift the random stream
+            generator.set_state(rng)
+        else:
+            torch.cuda.set_rng_state(rng, dev)
+        self.graph = torch.cuda.CUDAGraph()
+        if generator is not None:
+            self.graph.register_generator_state(generator)
+        from abx_b200 import lib
+        n0 = lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = step_fn(batch, self.t)
+        GraphedReverseStep.last_captured_launches = lib.launch_count() - n0     # abx kernels replayed per iteration
+        self._restore(snapshot)
+
+    def _restore(self, snapshot):
+        for k, v in snapshot.items():
+            self.state[k].copy_(v)
+            self.batch[k] = self.state[k]
+
+    def __call__(self, t):
+        self.t.fill_(float(t))
+        self.graph.replay()
+        new_state, model_out = self.out
+        for k in STATE_KEYS:
+            self.state[k].copy_(new_state[k])
+            self.batch[k] = self.state[k]
+        return model_out
+
+
 def sample_loop(data_init, config, diffuser, model, mode='design', num_t=100, min_t=0.01, center=True,
-                self_condition=True, noise_scale=1.0, eps=1e-8, noise_fn=None, generator=None, cache_static=True):
+                self_condition=True, noise_scale=1.0, eps=1e-8, noise_fn=None, generator=None, cache_static=True,
+                cuda_graph=False):
     """The loop of `sample_fn` without the PDB writing; returns (trajectory list, final batch).
-    `noise_fn(k) -> (z_rot, z_trans, jumps)` injects the k-th step's draws (teacher-forced parity)."""
+    `noise_fn(k) -> (z_rot, z_trans, jumps)` injects the k-th step's draws (teacher-forced parity).
+    `cuda_graph=True` replays the reverse iteration as a CUDA graph (needs self-conditioning features, i.e.
+    the default config; not combined with `noise_fn` or trajectory mode)."""
     config_model = config['model'] if isinstance(config, dict) else config.model
     embed_sc = config_model['heads']['diffusion_module']['embed']['embed_self_conditioning']
     batch = {k: (v.clone() if torch.is_tensor(v) else copy.deepcopy(v)) for k, v in data_init.items()}
@@ -75,19 +131,37 @@ def sample_loop(data_init, config, diffuser, model, mode='design', num_t=100, mi
                 batch = _set_t_feats(batch, diffuser, reverse_steps[0], t_placeholder, with_scalings=False)
                 batch = _self_conditioning(batch, model, config_model)
             data = None
+
+            def reverse_iteration(batch, t_, k=None):
+                """inference.py:215-242 for one t > min_t; returns (new state tensors, model_out)."""
+                _set_t_feats(batch, diffuser, t_, t_placeholder, with_scalings=False)
+                model_out = model(batch)
+                fold = model_out['heads']['folding']
+                if embed_sc:
+                    batch.update(get_prev(batch, model_out, config_model))
+                rigids_t, seq_t = diffuser.reverse(
+                    rigid_t=batch['rigids_t'], seq_t=batch['seq_t'], rot_score=fold['rot_score'],
+                    trans_score=fold['trans_score'], logits_t=model_out['heads']['sequence_module']['logits'],
+                    diffuse_mask=diffuse_mask, t=t_, dt=dt, center=center, noise_scale=noise_scale,
+                    noise=None if (noise_fn is None or k is None) else noise_fn(k), generator=generator)
+                new_state = {'rigids_t': rigids_t, 'seq_t': seq_t}
+                new_state.update({key: batch[key] for key in STATE_KEYS[2:] if key in batch})
+                return new_state, model_out
+
+            graphed = None
+            if cuda_graph and len(reverse_steps) > 2:
+                if noise_fn is not None or trajectory or not (embed_sc and self_condition):
+                    raise ValueError('cuda_graph=True needs the default self-conditioned design/optimize loop without noise_fn')
+                graphed = GraphedReverseStep(batch, reverse_iteration, generator=generator)
             for k, t in enumerate(reverse_steps):
                 if t > min_t:
-                    t_ = torch.full((B,), float(t), device=device, dtype=torch.float64)      # float64 (:216)
-                    batch = _set_t_feats(batch, diffuser, t_, t_placeholder, with_scalings=False)
-                    model_out = model(batch)
-                    fold = model_out['heads']['folding']
-                    if embed_sc:
-                        batch.update(get_prev(batch, model_out, config_model))
-                    rigids_t, seq_t = diffuser.reverse(
-                        rigid_t=batch['rigids_t'], seq_t=batch['seq_t'], rot_score=fold['rot_score'],
-                        trans_score=fold['trans_score'], logits_t=model_out['heads']['sequence_module']['logits'],
-                        diffuse_mask=diffuse_mask, t=t_, dt=dt, center=center, noise_scale=noise_scale,
-                        noise=None if noise_fn is None else noise_fn(k), generator=generator)
+                    if graphed is not None:
+                        model_out = graphed(t)
+                        rigids_t, seq_t = batch['rigids_t'], batch['seq_t']
+                    else:
+                        t_ = torch.full((B,), float(t), device=device, dtype=torch.float64)  # float64 (:216)
+                        new_state, model_out = reverse_iteration(batch, t_, k)
+                        rigids_t, seq_t = new_state['rigids_t'], new_state['seq_t']
                 else:
                     model_out = model(batch)                                                  # :244-247
                     rigids_t = model_out['heads']['folding']['rigids']
