@@ -164,3 +164,208 @@ extern "C" int abx_pair_attention(void* stream, int B, int S, int L, int H, int 
   set_error("abx_pair_attention: head dim %d not instantiated (16, 32, 48, 64)", D);
   return ABX_ERR_INVALID;
 }
+
+// =====================================================================================================
+// Tensor-core version of the same attention core: S = Q K^T and O = P V on mma.sync.m16n8k8 TF32 with the
+// 3xTF32 operand split (hi = x & ~0x1fff, lo = x - hi; hi*lo + lo*hi + hi*hi), i.e. fp32-level accuracy.
+// tcgen05 is not used here on purpose: the tiles are 16 x 8 x 8 fragments of a 350 x 350 x 48 problem per
+// (b,s,h) and live entirely in registers between the two products (FlashAttention-2 dataflow), which the
+// TMEM/descriptor model of tcgen05 does not fit without staging P through shared memory.
+//
+// One CTA per (b,s,h) and a group of up to 12 query tiles of 16 rows (one warp each).  K and V of the
+// (b,s,h) slice are staged once in shared memory with row stride D+4 floats, which makes every fragment
+// load of a warp hit 32 distinct banks.  Per 32-key chunk a warp computes four 16x8 score tiles (chained
+// in the tensor core over the D/8 k-steps), adds the pair bias, applies the key mask, updates the online
+// softmax per row (quad shuffles), and multiplies the probabilities with V; the accumulator layout of S
+// doubles as the A-operand layout of P V after relabelling the keys inside each group of 8
+// (k-index t <-> key 2t, k-index t+4 <-> key 2t+1), so no shuffles are needed between the two products.
+// =====================================================================================================
+namespace abx {
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+constexpr int kMmaMaxWarps = 12;
+
+template <int D>
+__global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) pair_attention_mma_kernel(
+    int L, int H, int S, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
+    const float* __restrict__ bias, const float* __restrict__ key_mask, float scale, float* __restrict__ out) {
+  constexpr int KS = D + 4, D4 = D / 4, NK = D / 8;   // smem row stride, float4 per row, k-steps of Q K^T (= n-tiles of P V)
+  extern __shared__ __align__(16) float sm[];
+  const int Lpad = (L + 31) & ~31;
+  float* Ks = sm;                                  // [Lpad][KS]
+  float* Vs = Ks + (size_t)Lpad * KS;              // [Lpad][KS]
+  float* Ms = Vs + (size_t)Lpad * KS;              // [Lpad] 1 keep / 0 masked
+  const int h = blockIdx.x, bs = blockIdx.y, b = bs / S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t row0 = (size_t)bs * L;
+
+  for (int idx = threadIdx.x; idx < Lpad * D4; idx += blockDim.x) {
+    const int j = idx / D4, d4 = idx % D4;
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+    if (j < L) {
+      const size_t gi = (row0 + j) * (size_t)ld + h * D + 4 * d4;
+      kk = *reinterpret_cast<const float4*>(k + gi);
+      vv = *reinterpret_cast<const float4*>(v + gi);
+    }
+    *reinterpret_cast<float4*>(Ks + (size_t)j * KS + 4 * d4) = kk;
+    *reinterpret_cast<float4*>(Vs + (size_t)j * KS + 4 * d4) = vv;
+  }
+  for (int j = threadIdx.x; j < Lpad; j += blockDim.x)
+    Ms[j] = (j < L) ? (key_mask ? __ldg(key_mask + (size_t)b * L + j) : 1.f) : 0.f;
+  __syncthreads();
+
+  const int r0 = (blockIdx.z * (blockDim.x >> 5) + warp) * 16;   // first query row of this warp
+  if (r0 >= L) return;
+  const int i0 = min(r0 + g, L - 1), i1 = min(r0 + g + 8, L - 1);
+
+  // Q fragments (scaled), split once
+  uint32_t qhi[NK][4], qlo[NK][4];
+  {
+    const float* q0 = q + (row0 + i0) * (size_t)ld + h * D;
+    const float* q1 = q + (row0 + i1) * (size_t)ld + h * D;
+#pragma unroll
+    for (int kk = 0; kk < NK; ++kk) {
+      split_tf32(__ldg(q0 + 8 * kk + t) * scale, qhi[kk][0], qlo[kk][0]);
+      split_tf32(__ldg(q1 + 8 * kk + t) * scale, qhi[kk][1], qlo[kk][1]);
+      split_tf32(__ldg(q0 + 8 * kk + t + 4) * scale, qhi[kk][2], qlo[kk][2]);
+      split_tf32(__ldg(q1 + 8 * kk + t + 4) * scale, qhi[kk][3], qlo[kk][3]);
+    }
+  }
+  float oacc[NK][4];
+#pragma unroll
+  for (int m = 0; m < NK; ++m) oacc[m][0] = oacc[m][1] = oacc[m][2] = oacc[m][3] = 0.f;
+  float m0 = -FLT_MAX, m1 = -FLT_MAX, l0 = 0.f, l1 = 0.f;      // running max / partial sum of rows g and g+8
+  const float* bias0 = bias + (((size_t)b * H + h) * L + i0) * L;
+  const float* bias1 = bias + (((size_t)b * H + h) * L + i1) * L;
+
+  for (int j0 = 0; j0 < Lpad; j0 += 32) {
+    // ---- S = Q K^T for 32 keys: four 16x8 tiles, chained over the D/8 k-steps in the tensor core
+    float s[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      const float* kr = Ks + (size_t)(j0 + 8 * n + g) * KS + t;
+#pragma unroll
+      for (int kk = 0; kk < NK; ++kk) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(kr[8 * kk], bh0, bl0);
+        split_tf32(kr[8 * kk + 4], bh1, bl1);
+        mma_tf32(s[n], qhi[kk], bl0, bl1);
+        mma_tf32(s[n], qlo[kk], bh0, bh1);
+        mma_tf32(s[n], qhi[kk], bh0, bh1);
+      }
+    }
+    // ---- bias, key mask, tail keys; row maxima
+    float cm0 = -FLT_MAX, cm1 = -FLT_MAX;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = j0 + 8 * n + 2 * t + e;
+        const bool valid = j < L;
+        const bool keep = Ms[j] != 0.f;
+        const float b0v = valid ? __ldg(bias0 + j) : 0.f, b1v = valid ? __ldg(bias1 + j) : 0.f;
+        float a0 = s[n][e] + b0v, a1 = s[n][2 + e] + b1v;
+        a0 = valid ? (keep ? a0 : -FLT_MAX) : -INFINITY;       // masked_fill(finfo.min); padding keys contribute exactly 0
+        a1 = valid ? (keep ? a1 : -FLT_MAX) : -INFINITY;
+        s[n][e] = a0; s[n][2 + e] = a1;
+        cm0 = fmaxf(cm0, a0); cm1 = fmaxf(cm1, a1);
+      }
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+    const float c0 = expf(m0 - mn0), c1 = expf(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int m = 0; m < NK; ++m) { oacc[m][0] *= c0; oacc[m][1] *= c0; oacc[m][2] *= c1; oacc[m][3] *= c1; }
+    // ---- P = exp(S - m); O += P V (per chunk chained in the tensor core, then added in fp32)
+    float pacc[NK][4];
+#pragma unroll
+    for (int m = 0; m < NK; ++m) pacc[m][0] = pacc[m][1] = pacc[m][2] = pacc[m][3] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float p00 = expf(s[n][0] - m0), p01 = expf(s[n][1] - m0), p10 = expf(s[n][2] - m1), p11 = expf(s[n][3] - m1);
+      l0 += p00 + p01; l1 += p10 + p11;
+      // A fragment of P for k-step n: (row g, k t) = key 2t, (row g+8, k t), (row g, k t+4) = key 2t+1, (row g+8, k t+4)
+      uint32_t phi[4], plo[4];
+      split_tf32(p00, phi[0], plo[0]); split_tf32(p10, phi[1], plo[1]);
+      split_tf32(p01, phi[2], plo[2]); split_tf32(p11, phi[3], plo[3]);
+      const float* vr = Vs + (size_t)(j0 + 8 * n + 2 * t) * KS + g;
+#pragma unroll
+      for (int m = 0; m < NK; ++m) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(vr[8 * m], bh0, bl0);             // V[key 2t][8m+g]
+        split_tf32(vr[KS + 8 * m], bh1, bl1);        // V[key 2t+1][8m+g]
+        mma_tf32(pacc[m], phi, bl0, bl1);
+        mma_tf32(pacc[m], plo, bh0, bh1);
+        mma_tf32(pacc[m], phi, bh0, bh1);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < NK; ++m) { oacc[m][0] += pacc[m][0]; oacc[m][1] += pacc[m][1]; oacc[m][2] += pacc[m][2]; oacc[m][3] += pacc[m][3]; }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  const size_t HD = (size_t)H * D;
+  if (r0 + g < L) {
+    float* o = out + (row0 + r0 + g) * HD + h * D + 2 * t;
+#pragma unroll
+    for (int m = 0; m < NK; ++m) *reinterpret_cast<float2*>(o + 8 * m) = make_float2(oacc[m][0] * inv0, oacc[m][1] * inv0);
+  }
+  if (r0 + g + 8 < L) {
+    float* o = out + (row0 + r0 + g + 8) * HD + h * D + 2 * t;
+#pragma unroll
+    for (int m = 0; m < NK; ++m) *reinterpret_cast<float2*>(o + 8 * m) = make_float2(oacc[m][2] * inv1, oacc[m][3] * inv1);
+  }
+}
+
+template <int D>
+static int launch_attention_mma(cudaStream_t st, int B, int S, int L, int H, const float* q, const float* k, const float* v,
+                                int ld, const float* bias, const float* key_mask, float* out) {
+  const int Lpad = (L + 31) & ~31;
+  const size_t smem = ((size_t)2 * Lpad * (D + 4) + Lpad) * sizeof(float);
+  ABX_REQUIRE(smem <= 227 * 1024, "abx_pair_attention: L=%d with head dim %d needs %zu bytes of shared memory (max 232448)", L, D, smem);
+  ABX_CUDA(cudaFuncSetAttribute(pair_attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (L + 15) / 16, nz = (tiles + kMmaMaxWarps - 1) / kMmaMaxWarps, warps = (tiles + nz - 1) / nz;
+  pair_attention_mma_kernel<D><<<dim3(H, B * S, nz), warps * 32, smem, st>>>(L, H, S, q, k, v, ld, bias, key_mask,
+                                                                               1.0f / sqrtf((float)D), out);
+  count_launch();
+  return check_launch("pair_attention_mma_kernel");
+}
+
+}  // namespace abx
+
+// impl: 0 = tensor-core kernel (default for D % 8 == 0), 1 = SIMT kernel
+extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, int D, const float* q, const float* k,
+                                       const float* v, int ld, const float* bias, const float* key_mask, float* out) {
+  using namespace abx;
+  if (impl == 1) return abx_pair_attention(stream, B, S, L, H, D, q, k, v, ld, bias, key_mask, out);
+  ABX_REQUIRE(B > 0 && S > 0 && L > 0 && H > 0 && q && k && v && bias && out, "abx_pair_attention: bad shape or null argument");
+  ABX_REQUIRE(ld % 4 == 0 && ld >= H * D, "abx_pair_attention: ld must be a multiple of 4 and >= H*D");
+  ABX_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 16 == 0),
+              "abx_pair_attention: q, k, v, out must be 16-byte aligned");
+  ABX_REQUIRE((long long)B * S <= 65535, "abx_pair_attention: B*S exceeds 65535");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (D) {
+    case 16: return launch_attention_mma<16>(st, B, S, L, H, q, k, v, ld, bias, key_mask, out);
+    case 32: return launch_attention_mma<32>(st, B, S, L, H, q, k, v, ld, bias, key_mask, out);
+    case 48: return launch_attention_mma<48>(st, B, S, L, H, q, k, v, ld, bias, key_mask, out);
+    case 64: return launch_attention_mma<64>(st, B, S, L, H, q, k, v, ld, bias, key_mask, out);
+  }
+  set_error("abx_pair_attention: head dim %d not instantiated (16, 32, 48, 64)", D);
+  return ABX_ERR_INVALID;
+}

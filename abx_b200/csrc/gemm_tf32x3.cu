@@ -191,7 +191,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
-                   int Nout, int K, Epilogue ep, float* __restrict__ y, int ldy, int trust_trunc) {
+                   int Nout, int K, Epilogue ep, float* __restrict__ y, int ldy, int trust_trunc, int kb_per_drain) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -260,15 +260,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     } else if (warp == 1 && lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-      uint32_t it = 0, lit[2] = {0, 0};               // lit[g]: k-slabs issued so far for accumulator WG g
+      // Partial sums: `kb_per_drain` consecutive k-slabs are chained in one TMEM buffer (the first MMA of a group
+      // overwrites), then handed to the accumulator WG, which adds them up in registers with round-to-nearest.
+      uint32_t it = 0, lit[2] = {0, 0};               // lit[g]: partial sums issued so far for accumulator WG g
       int j = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
         const int g = j & 1;
-        for (int kb = 0; kb < nkb; ++kb, ++it, ++lit[g]) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           const uint32_t buf = 2 * g + (lit[g] & 1), use = lit[g] >> 1;
-          mbar_wait(acc_free + buf, (use & 1) ^ 1);
+          const bool first = (kb % kb_per_drain) == 0, last = ((kb + 1) % kb_per_drain) == 0 || kb + 1 == nkb;
+          if (first) mbar_wait(acc_free + buf, (use & 1) ^ 1);
           mbar_wait(conv + s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tmem_acc = tmem_base + buf * BN;
@@ -277,13 +280,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // small cross terms first, then the hi*hi terms (UMMA_K = 8 tf32 = 32 bytes: +2 in the addr>>4 field)
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
-            umma_tf32(tmem_acc, a_hi + 2 * k, b_lo + 2 * k, idesc, k != 0);
+            umma_tf32(tmem_acc, a_hi + 2 * k, b_lo + 2 * k, idesc, (k != 0 || !first) ? 1u : 0u);
             umma_tf32(tmem_acc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
           }
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) umma_tf32(tmem_acc, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
           umma_commit(empty + s);                    // slab free once these MMAs have read it
-          umma_commit(acc_ready + buf);              // partial sum complete
+          if (last) {
+            umma_commit(acc_ready + buf);            // partial sum complete
+            ++lit[g];
+          }
         }
       }
     }
@@ -342,7 +348,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       float acc[BN];
 #pragma unroll
       for (int c = 0; c < BN; ++c) acc[c] = 0.f;
-      for (int kb = 0; kb < nkb; ++kb, ++lit) {
+      const int ngroups = (nkb + kb_per_drain - 1) / kb_per_drain;
+      for (int gi = 0; gi < ngroups; ++gi, ++lit) {
         const uint32_t buf = 2 * g + (lit & 1), use = lit >> 1;
         mbar_wait(acc_ready + buf, use & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -427,6 +434,14 @@ int trust_trunc() {
   return v;
 }
 
+// k-slabs (of 32) chained in tensor memory between two register accumulations: 1 = every slab (the tensor
+// core's truncating accumulator never chains more than 12 MMAs), larger values trade a little rounding bias for
+// fewer TMEM reads.  ABX_GEMM_KB_PER_DRAIN overrides the default.
+int kb_per_drain() {
+  static int v = [] { const char* e = getenv("ABX_GEMM_KB_PER_DRAIN"); int n = e ? atoi(e) : 1; return n < 1 ? 1 : (n > 64 ? 64 : n); }();
+  return v;
+}
+
 template <int BN>
 int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw, const Epilogue& ep,
               float* y, int ldy) {
@@ -442,7 +457,7 @@ int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, c
   }
   const int tiles = ceil_div(Nout, BN) * ceil_div(M, kBM);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tf32x3_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(ma, mb, M, Nout, K, ep, y, ldy, trust_trunc());
+  gemm_tf32x3_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(ma, mb, M, Nout, K, ep, y, ldy, trust_trunc(), kb_per_drain());
   count_launch();
   return check_launch("gemm_tf32x3_kernel");
 }

@@ -59,9 +59,10 @@ def layer_norm(x, weight, bias, eps=1e-5, transpose_n=0):
     return y
 
 
-def pair_attention(qkv, bias, key_mask, num_head):
+def pair_attention(qkv, bias, key_mask, num_head, impl='mma'):
     """Fused attention core for TriangleAttention.  qkv [B,S,L,3*H*D] (q | k | v slices of one projection),
-    bias [B,H,L,L], key_mask [B,L] (bool/float, None = keep all)  ->  [B,S,L,H*D]."""
+    bias [B,H,L,L], key_mask [B,L] (bool/float, None = keep all)  ->  [B,S,L,H*D].
+    impl: 'mma' (tensor cores, 3xTF32) or 'simt'."""
     L_ = lib.load()
     B, S, L, C3 = qkv.shape
     HD = C3 // 3
@@ -72,6 +73,7 @@ def pair_attention(qkv, bias, key_mask, num_head):
     out = torch.empty(B, S, L, HD, device=qkv.device, dtype=torch.float32)
     base, esz = qkv.data_ptr(), 4
     with lib.device_guard(qkv):
-        lib.check(L_.abx_pair_attention(lib.stream(), B, S, L, num_head, D, base, base + HD * esz, base + 2 * HD * esz, C3,
+        lib.check(L_.abx_pair_attention_impl(lib.stream(), {'mma': 0, 'simt': 1}[impl], B, S, L, num_head, D, base,
+                                             base + HD * esz, base + 2 * HD * esz, C3,
                                         lib.ptr(bias), lib.ptr(km), lib.ptr(out)))
     return out

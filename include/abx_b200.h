@@ -147,6 +147,10 @@ int abx_layernorm(void* stream, long long rows, int C, const float* x, const flo
  *   D in {16,32,48,64}; 2*L*D*4 bytes of K/V must fit in shared memory (L <= ~520 at D = 48). */
 int abx_pair_attention(void* stream, int B, int S, int L, int H, int D, const float* q, const float* k,
                        const float* v, int ld, const float* bias, const float* key_mask, float* out);
+/* Same operation with a choice of implementation: impl 0 = tensor-core kernel (mma.sync m16n8k8 TF32 with the
+ * 3xTF32 operand split, FlashAttention-2 dataflow in registers), impl 1 = the SIMT kernel above. */
+int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, int D, const float* q, const float* k,
+                            const float* v, int ld, const float* bias, const float* key_mask, float* out);
 
 /* Which GEMM the IPA pipeline uses for its node layers: 0 auto (tcgen05 when operands qualify),
  * 1 SIMT (abx_linear_f32), 2 tcgen05 only.  Process-wide; meant for A/B measurements and tests. */

@@ -41,8 +41,10 @@ def _attention_reference(qkv, bias, key_mask, H):
     return torch.einsum('bshqk,bshkd->bsqhd', w, v).reshape(B, S, L, H * D)
 
 
-@pytest.mark.parametrize('B,S,L,H,D', [(1, 3, 37, 4, 48), (2, 5, 350, 4, 48), (1, 2, 400, 2, 32), (1, 1, 1, 1, 16), (1, 2, 65, 3, 64)])
-def test_pair_attention_matches_reference(cuda_device, B, S, L, H, D):
+@pytest.mark.parametrize('impl', ['mma', 'simt'])
+@pytest.mark.parametrize('B,S,L,H,D', [(1, 3, 37, 4, 48), (2, 5, 350, 4, 48), (1, 2, 400, 2, 32), (1, 1, 1, 1, 16), (1, 2, 65, 3, 64),
+                                       (1, 2, 351, 4, 48)])
+def test_pair_attention_matches_reference(cuda_device, B, S, L, H, D, impl):
     from abx_b200 import ops
     qkv = np_randn(10, B, S, L, 3 * H * D).cuda()
     bias = (np_randn(11, B, H, L, L) * 2).cuda()
@@ -50,10 +52,10 @@ def test_pair_attention_matches_reference(cuda_device, B, S, L, H, D):
     if L > 8:
         mask[0, -5:] = False
         mask[-1, 3] = False
-    out = ops.pair_attention(qkv, bias, mask.cuda(), H)
+    out = ops.pair_attention(qkv, bias, mask.cuda(), H, impl=impl)
     ref = _attention_reference(qkv, bias, mask.cuda(), H)
     assert maxabs(out.cpu(), ref.cpu()) < 3e-6 * max(1.0, float(ref.abs().max()))
-    out2 = ops.pair_attention(qkv, bias, None, H)
+    out2 = ops.pair_attention(qkv, bias, None, H, impl=impl)
     ref2 = _attention_reference(qkv, bias, None, H)
     assert maxabs(out2.cpu(), ref2.cpu()) < 3e-6 * max(1.0, float(ref2.abs().max()))
 
@@ -64,10 +66,11 @@ def test_pair_attention_all_keys_masked_is_uniform(cuda_device):
     qkv = np_randn(12, 1, 2, 40, 3 * 4 * 48).cuda()
     bias = np_randn(13, 1, 4, 40, 40).cuda()
     mask = torch.zeros(1, 40, dtype=torch.bool).cuda()
-    out = ops.pair_attention(qkv, bias, mask, 4)
     ref = _attention_reference(qkv, bias, mask, 4)
-    assert torch.isfinite(out).all()
-    assert maxabs(out.cpu(), ref.cpu()) < 3e-6
+    for impl in ('mma', 'simt'):
+        out = ops.pair_attention(qkv, bias, mask, 4, impl=impl)
+        assert torch.isfinite(out).all()
+        assert maxabs(out.cpu(), ref.cpu()) < 3e-6
 
 
 def test_gemm_transposed_store(cuda_device):
