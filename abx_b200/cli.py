@@ -125,7 +125,7 @@ def run(args, raw_batches, rank=0, world=1):
         if rank == 0:
             _reference_batch(raw, args, os.path.join(root, 'reference'))
         for opt_step, out_root in plans:
-            fcfg = copy.deepcopy(feats)
+            fcfg = [[name, dict(kw)] for name, kw in feats]          # shallow: kw holds the diffuser object
             for name, kw in fcfg:
                 if name == 'make_diffuser_features':
                     kw['diffuser'] = diffuser

@@ -62,10 +62,17 @@ class IpaScore(nn.Module):
         init_quats, init_trans = init_rigids[..., :4], init_rigids[..., 4:]
         b, n = seq.shape
 
-        delta_quat, _ = quat_affine.make_identity(out_shape=(b, n), device=seq_act.device)
-        curr_quats = init_quats
-        curr_trans = init_trans / c.position_scale
-        curr_rots = quat_affine.quat_to_rot(curr_quats)
+        from abx_b200 import lib
+        L_ = lib.load()
+        dev = seq_act.device
+        delta_quat, _ = quat_affine.make_identity(out_shape=(b, n), device=dev)
+        init_quats = init_quats.contiguous()
+        init_trans_s = (init_trans / c.position_scale).contiguous()
+        fixed = batch['fixed_mask'].to(torch.int32).contiguous()
+        # frame state, updated in place by abx_ipa_frame_update each iteration
+        curr_quats = init_quats.clone()
+        curr_trans = init_trans_s.clone()
+        curr_rots = quat_affine.quat_to_rot(curr_quats).contiguous()
 
         seq_act = self.init_seq_layer_norm(self.proj_init_seq_act(seq_act))              # :117-120
         static_pair_act = self.init_pair_layer_norm(self.proj_init_pair_act(static_pair_act))
@@ -81,14 +88,13 @@ class IpaScore(nn.Module):
             seq_act = self.attention_layer_norm(seq_act)
             seq_act = self.transition_layer_norm(mlp(self.transition_module, seq_act, residual=seq_act))
 
-            quaternion_update, translation_update = self.affine_update(seq_act).chunk(2, dim=-1)
-            delta_quat = quat_affine.quat_precompose_vec(delta_quat, quaternion_update)
-            curr_quats = quat_affine.quat_precompose_vec(curr_quats, quaternion_update)
-            curr_trans = r3.rigids_mul_vecs((curr_rots, curr_trans), translation_update)
-            curr_quats = self._apply_mask(curr_quats, init_quats, keep)                  # :142-147
-            curr_trans = self._apply_mask(curr_trans, init_trans / c.position_scale, keep)
-            curr_rots = quat_affine.quat_to_rot(curr_quats)
-            outputs['traj'].append((curr_rots, curr_trans * c.position_scale))
+            upd = self.affine_update(seq_act)                            # [B,N,6] = (quaternion, translation) update
+            with lib.device_guard(upd):                                  # :137-149 in one launch
+                lib.check(L_.abx_ipa_frame_update(lib.stream(), b, n, lib.ptr(upd), lib.ptr(init_quats), lib.ptr(init_trans_s),
+                                                  lib.ptr(fixed), lib.ptr(delta_quat), lib.ptr(curr_quats), lib.ptr(curr_trans),
+                                                  lib.ptr(curr_rots)))
+            # the frame buffers are updated in place: the per-layer trajectory keeps copies
+            outputs['traj'].append((curr_rots if is_last else curr_rots.clone(), curr_trans * c.position_scale))
             if is_last:
                 outputs['sidechains'].append(self.sidechain_module(
                     seq, (curr_rots, curr_trans * c.position_scale), [seq_act, initial_seq_act], batch,

@@ -198,6 +198,16 @@ int abx_ipa_forward(void* stream, int B, int N, const float* x, const float* z, 
                     const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
                     const float* residual, float* out, void* workspace, size_t workspace_bytes);
 
+/* Frame update of one IpaScore iteration (score_network.py:137-149), in place, one launch:
+ *   upd [B,N,6] = affine_update(seq_act) = (quaternion update, translation update)
+ *   delta_quat, curr_quats [B,N,4] <- normalize(q + q (x) (0, upd[:3]))   (quat_affine.quat_precompose_vec)
+ *   curr_trans [B,N,3] (Angstrom / position_scale) <- curr_rots upd[3:] + curr_trans   (r3.rigids_mul_vecs)
+ *   residues with fixed_mask != 0 are reset to init_quats / init_trans (already / position_scale)
+ *   curr_rots [B,N,3,3] <- quat_to_rot(curr_quats) */
+int abx_ipa_frame_update(void* stream, int B, int N, const float* upd, const float* init_quats,
+                         const float* init_trans, const int32_t* fixed_mask, float* delta_quat, float* curr_quats,
+                         float* curr_trans, float* curr_rots);
+
 /* Stages of abx_ipa_forward, exported so tests and the benchmark can time/verify them separately. */
 /* feats [B,N,2112] = concat(o_scalar 192, o_point_local (r n) 288, o_point_norm 96, o_pair 1536) */
 int abx_ipa_attention_features(void* stream, int B, int N, const float* x, const float* z, const float* mask,
