@@ -191,7 +191,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
-                   int Nout, int K, Epilogue ep, float* __restrict__ y, int ldy, int trust_trunc, int kb_per_drain) {
+                   int Nout, int K, Epilogue ep, float* __restrict__ y, int ldy, int trust_trunc, int kb_per_drain,
+                   int splits, long long split_stride) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -209,9 +210,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (K + kBK - 1) / kBK;
+  // split-K: tile = (split, m block, n block); split s covers k-slabs [s kbs, min((s+1) kbs, total)) and writes its
+  // raw partial product to y + s split_stride (the caller reduces); splits == 1 is the plain GEMM
+  const int nkb_total = (K + kBK - 1) / kBK;
+  const int kbs = (nkb_total + splits - 1) / splits;
   const int nt = (Nout + BN - 1) / BN, mt = (M + kBM - 1) / kBM;
-  const int tiles = nt * mt;
+  const int mnt = nt * mt, tiles = mnt * splits;
+  auto tile_nkb = [&](int tile) { const int k0 = (tile / mnt) * kbs; return min(kbs, nkb_total - k0); };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -247,14 +252,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // ---------------- TMA producer ----------------
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m0 = (tile / nt) * kBM, n0 = (tile % nt) * BN;
+        const int rem = tile % mnt, kb0 = (tile / mnt) * kbs, nkb = tile_nkb(tile);
+        const int m0 = (rem / nt) * kBM, n0 = (rem % nt) * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(empty + s, ph ^ 1);
           mbar_expect_tx(full + s, kTileABytes + Cfg::kTileBBytes);
-          tma_load_2d(stage_a(s), &map_a, full + s, kb * kBK, m0);
-          tma_load_2d(stage_b(s), &map_b, full + s, kb * kBK, n0);
+          tma_load_2d(stage_a(s), &map_a, full + s, (kb0 + kb) * kBK, m0);
+          tma_load_2d(stage_b(s), &map_b, full + s, (kb0 + kb) * kBK, n0);
         }
       }
     } else if (warp == 1 && lane == 0) {
@@ -266,6 +272,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       int j = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
         const int g = j & 1;
+        const int nkb = tile_nkb(tile);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -278,6 +285,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint64_t a_hi = umma_desc_sw128(smem_u32(stage_a(s))), a_lo = umma_desc_sw128(smem_u32(stage_alo(s)));
           const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_b(s))), b_lo = umma_desc_sw128(smem_u32(stage_blo(s)));
           // small cross terms first, then the hi*hi terms (UMMA_K = 8 tf32 = 32 bytes: +2 in the addr>>4 field)
+          if (!(trust_trunc & 4)) {
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             umma_tf32(tmem_acc, a_hi + 2 * k, b_lo + 2 * k, idesc, (k != 0 || !first) ? 1u : 0u);
@@ -285,6 +293,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) umma_tf32(tmem_acc, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+          }
           umma_commit(empty + s);                    // slab free once these MMAs have read it
           if (last) {
             umma_commit(acc_ready + buf);            // partial sum complete
@@ -299,10 +308,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int ct = threadIdx.x - 128;                // 0..127
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int nkb = tile_nkb(tile);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(full + s, ph);
+        if (trust_trunc & 2) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); mbar_arrive(conv + s); continue; }
         auto split = [&](float4* hi_p, float4* lo_p, int i) {
           float4 v = hi_p[i], h, l;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
@@ -310,7 +321,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
           h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
           l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          if (!trust_trunc) hi_p[i] = h;
+          if (!(trust_trunc & 1)) hi_p[i] = h;
           lo_p[i] = l;
         };
         float4* a = reinterpret_cast<float4*>(stage_a(s));
@@ -336,7 +347,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         (!ep.gate || (reinterpret_cast<uintptr_t>(ep.gate) & 15) == 0);
     uint32_t lit = 0;                                // k-slabs this WG has drained (its own phase counter)
     for (int tile = blockIdx.x + g * gridDim.x; tile < tiles; tile += 2 * gridDim.x) {
-      const int m0 = (tile / nt) * kBM, n0 = (tile % nt) * BN;
+      const int rem = tile % mnt, nkb = tile_nkb(tile);
+      const int m0 = (rem / nt) * kBM, n0 = (rem % nt) * BN;
+      float* __restrict__ yt = y + (long long)(tile / mnt) * split_stride;
       const int row = m0 + 32 * q + lane;
       if (row < M) {                                 // pull this row's gate / residual pieces into L2 ahead of the epilogue
         const int ncol = min(BN, Nout - n0);
@@ -355,6 +368,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (trust_trunc & 8) break;
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + buf * BN + (uint32_t)c0, v);
 #pragma unroll
@@ -365,11 +379,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       if (row < M) {
         switch (ep.act) {
-          case 0: store_row<0, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
-          case 1: store_row<1, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
-          case 2: store_row<2, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
-          case 3: store_row<3, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
-          default: store_row<4, BN>(acc, ep, y, ldy, row, n0, Nout, vec_ok); break;
+          case 0: store_row<0, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
+          case 1: store_row<1, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
+          case 2: store_row<2, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
+          case 3: store_row<3, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
+          default: store_row<4, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
         }
       }
     }
@@ -430,7 +444,11 @@ int sm_count() {
 // tools/gemm_trunc_probe.py), so the raw fp32 tile already acts as the hi part and the converters only write
 // the lo tile.  ABX_GEMM_TRUST_TRUNC=0 restores the explicit hi write-back.
 int trust_trunc() {
-  static int v = [] { const char* e = getenv("ABX_GEMM_TRUST_TRUNC"); return (e && e[0] == '0') ? 0 : 1; }();
+  static int v = [] {
+    const char* e = getenv("ABX_GEMM_TRUST_TRUNC");
+    const char* d = getenv("ABX_GEMM_DEBUG_SKIP");      // timing experiments only: 2 skip split, 4 skip MMA, 8 skip drain
+    return ((e && e[0] == '0') ? 0 : 1) | (d ? (atoi(d) & 14) : 0);
+  }();
   return v;
 }
 
@@ -444,7 +462,7 @@ int kb_per_drain() {
 
 template <int BN>
 int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw, const Epilogue& ep,
-              float* y, int ldy) {
+              float* y, int ldy, int splits = 1, long long split_stride = 0) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ma, mb;
   int rc;
@@ -455,9 +473,10 @@ int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, c
     ABX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ceil_div(Nout, BN) * ceil_div(M, kBM);
+  const int tiles = ceil_div(Nout, BN) * ceil_div(M, kBM) * splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tf32x3_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(ma, mb, M, Nout, K, ep, y, ldy, trust_trunc(), kb_per_drain());
+  gemm_tf32x3_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(ma, mb, M, Nout, K, ep, y, ldy, trust_trunc(), kb_per_drain(),
+                                                                 splits, split_stride);
   count_launch();
   return check_launch("gemm_tf32x3_kernel");
 }
@@ -488,6 +507,24 @@ int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, i
   }
   set_error("abx_gemm_tf32x3: tile_n must be 0, 32, 64 or 128 (got %d)", tile_n);
   return ABX_ERR_INVALID;
+}
+
+// Split-K form for skinny problems (few output tiles, long K — IPA's final projection): `splits` raw partial
+// products x W^T restricted to consecutive K ranges are written to partials[s][M][Nout]; the caller sums them.
+int launch_gemm_tf32x3_splitk(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                              int* splits_io, float* partials, int tile_n) {
+  int splits = *splits_io;
+  const int nkb = ceil_div(K, kBK);
+  if (splits > nkb) splits = nkb;
+  while (splits > 1 && (splits - 1) * ceil_div(nkb, splits) >= nkb) --splits;   // no empty split
+  *splits_io = splits;
+  Epilogue ep{nullptr, nullptr, nullptr, nullptr, 0, 0};
+  const long long stride = (long long)M * Nout;
+  switch (tile_n) {
+    case 32: return launch_bn<32>(s, M, Nout, K, x, ldx, w, ldw, ep, partials, Nout, splits, stride);
+    case 64: return launch_bn<64>(s, M, Nout, K, x, ldx, w, ldw, ep, partials, Nout, splits, stride);
+    default: return launch_bn<128>(s, M, Nout, K, x, ldx, w, ldw, ep, partials, Nout, splits, stride);
+  }
 }
 
 }  // namespace abx

@@ -20,6 +20,10 @@ namespace abx {
 
 int launch_linear_f32(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w,
                       const float* bias, const float* residual, int relu, float* y, int ldy);
+bool gemm_tf32x3_supported(int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw);
+int launch_gemm_tf32x3_splitk(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                              int* splits_io, float* partials, int tile_n);
+int gemm_backend();
 
 constexpr int kH = ABX_IPA_H, kC = ABX_IPA_C, kCz = ABX_IPA_CZ, kFeat = ABX_IPA_FEAT;
 constexpr int kSqk = 16, kSv = 16, kPqk = 4, kPv = 8;
@@ -41,49 +45,53 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {   // streaming r
 }
 
 // ---------------------------------------------------------------------------------------------------
-// pack: one thread per (b, n, h).  proj row -> Qdat/Kdat/Vdat with the points moved to the global frame
-// (r3.rigids_apply, r3.py:9-16) and the query scalars pre-multiplied by sqrt(1/(3*16)) (folding.py:59,79).
+// pack: proj row -> Qdat/Kdat/Vdat with the points moved to the global frame (r3.rigids_apply, r3.py:9-16) and
+// the query scalars pre-multiplied by sqrt(1/(3*16)) (folding.py:59,79).  One thread per (b, n, h, item):
+// items 0-3 / 4-7 / 8-11 = float4 groups of the q / k / v scalars, 12-15 / 16-19 / 20-27 = q / k / v points.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ipa_pack_kernel(int B, int N, const float* __restrict__ proj,
+constexpr int kPackItems = 3 * (kSqk / 4) + 2 * kPqk + kPv;   // 28
+
+__global__ void __launch_bounds__(256) ipa_pack_kernel(int B, int N, const float* __restrict__ proj,
                                                        const float* __restrict__ rots, const float* __restrict__ trans,
                                                        float* __restrict__ Qdat, float* __restrict__ Kdat,
                                                        float* __restrict__ Vdat) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * N * kH) return;
-  const int h = idx % kH, bn = idx / kH, b = bn / N, n = bn % N;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N * kH * kPackItems) return;
+  const int item = idx % kPackItems, rest = idx / kPackItems;
+  const int h = rest % kH, bn = rest / kH, b = bn / N, n = bn % N;
   const float* row = proj + (size_t)bn * kProj;
-  float R[9], t[3];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = rots[(size_t)bn * 9 + k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) t[k] = trans[(size_t)bn * 3 + k];
   const size_t o = ((size_t)(b * kH + h) * N + n);
-  float* q = Qdat + o * kQK;
-  float* kk = Kdat + o * kQK;
-  float* v = Vdat + o * kVD;
-  const float w_scalar = sqrtf(1.0f / (3.0f * kSqk));
-#pragma unroll
-  for (int c = 0; c < kSqk; ++c) q[c] = row[h * kSqk + c] * w_scalar;
-#pragma unroll
-  for (int c = 0; c < kSqk; ++c) kk[c] = row[kOffKV + h * (kSqk + kSv) + c];
-#pragma unroll
-  for (int c = 0; c < kSv; ++c) v[c] = row[kOffKV + h * (kSqk + kSv) + kSqk + c];
-  auto apply = [&](float lx, float ly, float lz, float* out) {
-    out[0] = t[0] + (R[0] * lx + R[1] * ly + R[2] * lz);
-    out[1] = t[1] + (R[3] * lx + R[4] * ly + R[5] * lz);
-    out[2] = t[2] + (R[6] * lx + R[7] * ly + R[8] * lz);
-  };
-#pragma unroll
-  for (int p = 0; p < kPqk; ++p) {   // channel layout '(r n)', n = (h p)   folding.py:82,91
-    const float* l = row + kOffQP + h * kPqk + p;
-    apply(l[0], l[kH * kPqk], l[2 * kH * kPqk], q + kSqk + 3 * p);
+  if (item < 12) {                                   // scalar channels, 4 at a time
+    const int grp = item >> 2, c = 4 * (item & 3);
+    if (grp == 0) {
+      const float w_scalar = sqrtf(1.0f / (3.0f * kSqk));
+      const float4 v = *reinterpret_cast<const float4*>(row + h * kSqk + c);
+      *reinterpret_cast<float4*>(Qdat + o * kQK + c) = make_float4(v.x * w_scalar, v.y * w_scalar, v.z * w_scalar, v.w * w_scalar);
+    } else if (grp == 1) {
+      *reinterpret_cast<float4*>(Kdat + o * kQK + c) = *reinterpret_cast<const float4*>(row + kOffKV + h * (kSqk + kSv) + c);
+    } else {
+      *reinterpret_cast<float4*>(Vdat + o * kVD + c) = *reinterpret_cast<const float4*>(row + kOffKV + h * (kSqk + kSv) + kSqk + c);
+    }
+    return;
   }
-#pragma unroll
-  for (int p = 0; p < kPqk + kPv; ++p) {   // per head: 4 key points then 8 value points   folding.py:93
-    const float* l = row + kOffKVP + h * (kPqk + kPv) + p;
-    float* dst = (p < kPqk) ? (kk + kSqk + 3 * p) : (v + kSv + 3 * (p - kPqk));
-    apply(l[0], l[kH * (kPqk + kPv)], l[2 * kH * (kPqk + kPv)], dst);
+  // one point: local coordinates are channel-major '(r n)', n = (h p)   folding.py:82,91,93
+  const float* l;
+  int stride;
+  float* dst;
+  if (item < 16) {
+    const int p = item - 12;
+    l = row + kOffQP + h * kPqk + p; stride = kH * kPqk; dst = Qdat + o * kQK + kSqk + 3 * p;
+  } else {
+    const int p = item - 16;                         // per head: 4 key points then 8 value points
+    l = row + kOffKVP + h * (kPqk + kPv) + p; stride = kH * (kPqk + kPv);
+    dst = (p < kPqk) ? (Kdat + o * kQK + kSqk + 3 * p) : (Vdat + o * kVD + kSv + 3 * (p - kPqk));
   }
+  const float lx = l[0], ly = l[stride], lz = l[2 * stride];
+  const float* R = rots + (size_t)bn * 9;
+  const float* t = trans + (size_t)bn * 3;
+  dst[0] = __ldg(t + 0) + (__ldg(R + 0) * lx + __ldg(R + 1) * ly + __ldg(R + 2) * lz);
+  dst[1] = __ldg(t + 1) + (__ldg(R + 3) * lx + __ldg(R + 4) * ly + __ldg(R + 5) * lz);
+  dst[2] = __ldg(t + 2) + (__ldg(R + 6) * lx + __ldg(R + 7) * ly + __ldg(R + 8) * lz);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -411,10 +419,18 @@ __host__ inline size_t agg_smem_bytes(int N) {
 // ---------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
+constexpr int kMaxSplits = 6;   // split-K factor of the final projection (2112 -> 256) when B*N is small
+
 struct IpaWorkspace {
-  float *proj, *Qdat, *Kdat, *Vdat, *probs, *feats, *bias;
+  float *proj, *Qdat, *Kdat, *Vdat, *probs, *feats, *bias, *partials;
   size_t total;
 };
+
+static int final_proj_splits(int M) {
+  const int tiles = ceil_div(M, 128) * (kC / 32);
+  int s = ceil_div(2 * 148, tiles);
+  return s < 1 ? 1 : (s > kMaxSplits ? kMaxSplits : s);
+}
 
 static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_feats) {
   IpaWorkspace w;
@@ -428,6 +444,7 @@ static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_fe
   w.Vdat = take(bn * kH * kVD);
   w.probs = take(bn * kH * N);
   w.feats = with_feats ? take(bn * kFeat) : nullptr;
+  w.partials = (with_feats && final_proj_splits((int)bn) > 1) ? take((size_t)final_proj_splits((int)bn) * bn * kC) : nullptr;
   w.bias = with_bias ? take(bn * kH * N) : nullptr;
   w.total = off;
   return w;
@@ -448,7 +465,7 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   if ((rc = launch_linear_f32(s, M, 3 * kH * kPqk, kC, x, kC, w->w_q_point, w->b_q_point, nullptr, 0, ws.proj + kOffQP, kProj))) return rc;
   if ((rc = launch_linear_f32(s, M, 3 * kH * (kPqk + kPv), kC, x, kC, w->w_kv_point, w->b_kv_point, nullptr, 0, ws.proj + kOffKVP, kProj))) return rc;
   }
-  ipa_pack_kernel<<<ceil_div(M * kH, 128), 128, 0, s>>>(B, N, ws.proj, rots, trans, ws.Qdat, ws.Kdat, ws.Vdat);
+  ipa_pack_kernel<<<ceil_div(M * kH * kPackItems, 256), 256, 0, s>>>(B, N, ws.proj, rots, trans, ws.Qdat, ws.Kdat, ws.Vdat);
   count_launch();
   if ((rc = check_launch("ipa_pack_kernel"))) return rc;
 
@@ -471,6 +488,22 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   ipa_pair_aggregate_kernel<<<dim3(N, B), kAggThreads, gsmem, s>>>(N, z, ws.probs, feats);
   count_launch();
   return check_launch("ipa_pair_aggregate_kernel");
+}
+
+// out = sum_s partials[s] + bias (+ residual): the reduction of the split-K final projection
+__global__ void __launch_bounds__(256) ipa_finalize_kernel(int MN4, int splits, const float4* __restrict__ partials,
+                                                           const float4* __restrict__ bias, const float4* __restrict__ residual,
+                                                           float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN4) return;
+  float4 a = partials[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 p = partials[(size_t)s * MN4 + i];
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+  }
+  if (bias) { const float4 b = __ldg(bias + (i % (kC / 4))); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  if (residual) { const float4 r = residual[i]; a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
+  out[i] = a;
 }
 
 static int ipa_check(const char* fn, int B, int N, const void* x, const void* z, const void* mask, const void* rots,
@@ -522,6 +555,19 @@ extern "C" int abx_ipa_forward(void* stream, int B, int N, const float* x, const
   ABX_REQUIRE(workspace_bytes >= ws.total, "abx_ipa_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = ipa_features(s, B, N, x, z, mask, rots, trans, w, pair_bias, ws.feats, ws))) return rc;
-  // final_proj (folding.py:130-132) with the residual of score_network.py:128 fused into the epilogue
-  return launch_linear_f32(s, B * N, kC, kFeat, ws.feats, kFeat, w->w_final, w->b_final, residual, 0, out, kC);
+  // final_proj (folding.py:130-132) + the residual of score_network.py:128.  With few rows the 2112-long
+  // reduction is split across CTAs (split-K) and summed by a small kernel; otherwise one GEMM with fused epilogue.
+  const int M = B * N;
+  int splits = final_proj_splits(M);
+  const bool vec = ((uintptr_t)out % 16 == 0) && (!residual || (uintptr_t)residual % 16 == 0) && (!w->b_final || (uintptr_t)w->b_final % 16 == 0);
+  if (splits > 1 && ws.partials && vec && gemm_backend() != 1 && gemm_tf32x3_supported(M, kC, kFeat, ws.feats, kFeat, w->w_final, kFeat)) {
+    if ((rc = launch_gemm_tf32x3_splitk(s, M, kC, kFeat, ws.feats, kFeat, w->w_final, kFeat, &splits, ws.partials, 32))) return rc;
+    const int MN4 = M * kC / 4;
+    ipa_finalize_kernel<<<ceil_div(MN4, 256), 256, 0, s>>>(MN4, splits, reinterpret_cast<const float4*>(ws.partials),
+                                                          reinterpret_cast<const float4*>(w->b_final),
+                                                          reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out));
+    count_launch();
+    return check_launch("ipa_finalize_kernel");
+  }
+  return launch_linear_f32(s, M, kC, kFeat, ws.feats, kFeat, w->w_final, w->b_final, residual, 0, out, kC);
 }

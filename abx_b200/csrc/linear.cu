@@ -99,6 +99,7 @@ int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, i
                        int transpose_n, float* y, int ldy, int tile_n);
 
 static int g_backend = 0;   // 0 auto (tensor cores when the operands qualify), 1 SIMT only, 2 tensor cores only
+int gemm_backend() { return g_backend; }
 
 // Dense layer dispatcher used by the IPA pipeline: 3xTF32 tcgen05 GEMM (gemm_tf32x3.cu) when the operand
 // layout allows TMA, else the SIMT kernel below.
