@@ -182,17 +182,6 @@ extern "C" int abx_pair_attention(void* stream, int B, int S, int L, int H, int 
 // =====================================================================================================
 namespace abx {
 
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-
 constexpr int kMmaMaxWarps = 12;
 
 template <int D>
@@ -253,18 +242,23 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) pair_attention_mma_kerne
     // ---- S = Q K^T for 32 keys: four 16x8 tiles, chained over the D/8 k-steps in the tensor core
     float s[4][4];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-      const float* kr = Ks + (size_t)(j0 + 8 * n + g) * KS + t;
+    for (int n = 0; n < 4; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    // k-step outer, score tile inner: consecutive MMAs go to different accumulators (4 independent chains)
 #pragma unroll
-      for (int kk = 0; kk < NK; ++kk) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(kr[8 * kk], bh0, bl0);
-        split_tf32(kr[8 * kk + 4], bh1, bl1);
-        mma_tf32(s[n], qhi[kk], bl0, bl1);
-        mma_tf32(s[n], qlo[kk], bh0, bh1);
-        mma_tf32(s[n], qhi[kk], bh0, bh1);
+    for (int kk = 0; kk < NK; ++kk) {
+      uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const float* kr = Ks + (size_t)(j0 + 8 * n + g) * KS + t + 8 * kk;
+        split_tf32(kr[0], bh0[n], bl0[n]);
+        split_tf32(kr[4], bh1[n], bl1[n]);
       }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_tf32(s[n], qhi[kk], bl0[n], bl1[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_tf32(s[n], qlo[kk], bh0[n], bh1[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_tf32(s[n], qhi[kk], bh0[n], bh1[n]);
     }
     // ---- bias, key mask, tail keys; row maxima
     float cm0 = -FLT_MAX, cm1 = -FLT_MAX;
@@ -304,15 +298,18 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) pair_attention_mma_kerne
       split_tf32(p00, phi[0], plo[0]); split_tf32(p10, phi[1], plo[1]);
       split_tf32(p01, phi[2], plo[2]); split_tf32(p11, phi[3], plo[3]);
       const float* vr = Vs + (size_t)(j0 + 8 * n + 2 * t) * KS + g;
+      uint32_t vh0[NK], vl0[NK], vh1[NK], vl1[NK];
 #pragma unroll
       for (int m = 0; m < NK; ++m) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(vr[8 * m], bh0, bl0);             // V[key 2t][8m+g]
-        split_tf32(vr[KS + 8 * m], bh1, bl1);        // V[key 2t+1][8m+g]
-        mma_tf32(pacc[m], phi, bl0, bl1);
-        mma_tf32(pacc[m], plo, bh0, bh1);
-        mma_tf32(pacc[m], phi, bh0, bh1);
+        split_tf32(vr[8 * m], vh0[m], vl0[m]);             // V[key 2t][8m+g]
+        split_tf32(vr[KS + 8 * m], vh1[m], vl1[m]);        // V[key 2t+1][8m+g]
       }
+#pragma unroll
+      for (int m = 0; m < NK; ++m) mma_tf32(pacc[m], phi, vl0[m], vl1[m]);
+#pragma unroll
+      for (int m = 0; m < NK; ++m) mma_tf32(pacc[m], plo, vh0[m], vh1[m]);
+#pragma unroll
+      for (int m = 0; m < NK; ++m) mma_tf32(pacc[m], phi, vh0[m], vh1[m]);
     }
 #pragma unroll
     for (int m = 0; m < NK; ++m) { oacc[m][0] += pacc[m][0]; oacc[m][1] += pacc[m][1]; oacc[m][2] += pacc[m][2]; oacc[m][3] += pacc[m][3]; }

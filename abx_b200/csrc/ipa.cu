@@ -13,6 +13,7 @@
 // probabilities and pair bias head-major [B,H,N,N] so that both the attention kernel (fixed h, rows of
 // j) and the aggregation kernel (fixed i, 12 rows of j) read contiguous runs.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -342,6 +343,256 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------------
+// attention on the tensor cores (default): one warp per 16 query rows, FlashAttention-2 style fragments
+// (mma.sync m16n8k8 TF32, 3xTF32 operand split = fp32-level accuracy).
+//   logit = q_s.k_s + coef |Q-K|^2 + bias = [q_s, -2 coef Q] . [k_s, K] + coef |Q|^2 + coef |K|^2 + bias
+// i.e. one 28-long (padded to 32) inner product plus a row term and a key term, so the O(N^2) part is an MMA.
+// Pass 1 accumulates the row maximum and sum (online), pass 2 recomputes the scores, writes the normalised
+// probabilities (for the pair aggregation kernel) and multiplies them with the 40-wide value rows.  The key
+// and value rows of the (b,h) slice are staged once per CTA in shared memory (row strides 36 / 44 floats:
+// conflict-free fragment loads).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMW = 8;                     // warps (16-row tiles) per CTA
+constexpr int kKS = 36, kVS = 44;          // smem row strides of the key (32 used) and value (40 used) rows
+
+__host__ __device__ inline size_t attn_mma_smem_floats(int N) {
+  const int Np = (N + 31) & ~31;
+  return (size_t)Np * (kKS + kVS) + 2 * (size_t)Np + (size_t)kMW * 16 * (kVD + 1);
+}
+
+__global__ void __launch_bounds__(kMW * 32) ipa_attention_mma_kernel(
+    int N, const float* __restrict__ Qdat, const float* __restrict__ Kdat, const float* __restrict__ Vdat,
+    const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
+    const float* __restrict__ trans, const float* __restrict__ point_weights, float* __restrict__ probs,
+    float* __restrict__ feats) {
+  extern __shared__ __align__(16) float sm[];
+  const int Np = (N + 31) & ~31;
+  float* Ks = sm;                            // [Np][36]: k_s (16), K points (12), zeros (8)
+  float* Vs = Ks + (size_t)Np * kKS;         // [Np][44]: v_s (16), V points (24), pad
+  float* Ck = Vs + (size_t)Np * kVS;         // [Np] coef |K_j|^2
+  float* Ms = Ck + Np;                       // [Np] mask_j
+  float* Ot = Ms + Np;                       // per warp [16][41] output tile
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const size_t bh = (size_t)b * kH + h;
+  const float pw = __ldg(point_weights + h);
+  const float gamma = (pw > 20.f) ? pw : log1pf(expf(pw));                        // F.softplus  folding.py:96
+  const float coef = -0.5f * sqrtf(1.0f / (3.0f * kPqk * 9.0f / 2.0f)) * gamma;   // -1/2 w_point gamma  :97-99
+
+  // stage the packed key / value rows with cp.async (all copies in flight at once); pad columns and rows are zeroed
+  for (int idx = threadIdx.x; idx < Np * (kKS / 4); idx += blockDim.x) {
+    const int j = idx / (kKS / 4), c4 = idx % (kKS / 4);
+    float* dst = Ks + (size_t)j * kKS + 4 * c4;
+    if (j < N && c4 < kQK / 4) cp_async16(dst, Kdat + (bh * N + j) * kQK + 4 * c4);
+    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int idx = threadIdx.x; idx < Np * (kVS / 4); idx += blockDim.x) {
+    const int j = idx / (kVS / 4), c4 = idx % (kVS / 4);
+    float* dst = Vs + (size_t)j * kVS + 4 * c4;
+    if (j < N && c4 < kVD / 4) cp_async16(dst, Vdat + (bh * N + j) * kVD + 4 * c4);
+    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int j = threadIdx.x; j < Np; j += blockDim.x) {
+    float s2 = 0.f;
+    if (j < N) {
+#pragma unroll
+      for (int c = kSqk; c < kQK; ++c) { const float kv = Ks[(size_t)j * kKS + c]; s2 = fmaf(kv, kv, s2); }
+    }
+    Ck[j] = coef * s2;
+    Ms[j] = (j < N) ? __ldg(mask + (size_t)b * N + j) : 0.f;
+  }
+  __syncthreads();
+
+  const int r0 = (blockIdx.x * kMW + warp) * 16;
+  if (r0 >= N) return;
+  const int i0 = min(r0 + g, N - 1), i1 = min(r0 + g + 8, N - 1);
+  // A fragments of [q_s, -2 coef Q, 0]: 4 k-steps of 8; row terms coef |Q_i|^2
+  uint32_t qhi[4][4], qlo[4][4];
+  float cq0 = 0.f, cq1 = 0.f;
+  {
+    const float* q0 = Qdat + (bh * N + i0) * kQK;
+    const float* q1 = Qdat + (bh * N + i1) * kQK;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = 8 * kk + t + 4 * e;
+        float a0 = 0.f, a1 = 0.f;
+        if (c < kQK) { a0 = __ldg(q0 + c); a1 = __ldg(q1 + c); }
+        if (c >= kSqk && c < kQK) { a0 *= -2.f * coef; a1 *= -2.f * coef; }
+        split_tf32(a0, qhi[kk][2 * e], qlo[kk][2 * e]);
+        split_tf32(a1, qhi[kk][2 * e + 1], qlo[kk][2 * e + 1]);
+      }
+    }
+    for (int c = kSqk; c < kQK; ++c) { const float a0 = __ldg(q0 + c), a1 = __ldg(q1 + c); cq0 = fmaf(a0, a0, cq0); cq1 = fmaf(a1, a1, cq1); }
+    cq0 *= coef; cq1 *= coef;
+  }
+  const float mi0 = __ldg(mask + (size_t)b * N + i0), mi1 = __ldg(mask + (size_t)b * N + i1);
+  const float* bias0 = bias + (bh * N + i0) * N;
+  const float* bias1 = bias + (bh * N + i1) * N;
+
+  // bias values of a 32-key chunk in fragment order (row g: [n][e], row g+8: [n][2+e]); loaded one chunk ahead
+  auto load_bias = [&](int j0, float (&bv)[4][4]) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = j0 + 8 * n + 2 * t + e;
+        const bool valid = j < N;
+        bv[n][e] = valid ? __ldg(bias0 + j) : 0.f;
+        bv[n][2 + e] = valid ? __ldg(bias1 + j) : 0.f;
+      }
+  };
+  constexpr float kLog2e = 1.4426950408889634f;
+  auto scores = [&](int j0, const float (&bv)[4][4], float (&s)[4][4]) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    // k-step outer, score tile inner: consecutive MMAs go to different accumulators (4 independent chains)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const float* kr = Ks + (size_t)(j0 + 8 * n + g) * kKS + t + 8 * kk;
+        split_tf32(kr[0], bh0[n], bl0[n]);
+        split_tf32(kr[4], bh1[n], bl1[n]);
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_tf32(s[n], qhi[kk], bl0[n], bl1[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_tf32(s[n], qlo[kk], bh0[n], bh1[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) mma_tf32(s[n], qhi[kk], bh0[n], bh1[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = j0 + 8 * n + 2 * t + e;
+        const bool valid = j < N;
+        const float ck = Ck[j], mj = Ms[j];
+        float a0 = (((s[n][e] + cq0) + ck) + bv[n][e]) * kLog2e;          // logits in units of log 2: exp(x) = exp2(x log2 e)
+        float a1 = (((s[n][2 + e] + cq1) + ck) + bv[n][2 + e]) * kLog2e;
+        a0 = valid ? ((mi0 * mj != 0.f) ? a0 : -FLT_MAX) : -INFINITY;     // mask_2d  folding.py:106-109
+        a1 = valid ? ((mi1 * mj != 0.f) ? a1 : -FLT_MAX) : -INFINITY;
+        s[n][e] = a0; s[n][2 + e] = a1;
+      }
+    }
+  };
+
+  // ---- pass 1: row maximum and sum of exponentials
+  float m0 = -FLT_MAX, m1 = -FLT_MAX, l0 = 0.f, l1 = 0.f;
+  float bnext[4][4];
+  load_bias(0, bnext);
+  for (int j0 = 0; j0 < Np; j0 += 32) {
+    float s[4][4], bcur[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { bcur[n][0] = bnext[n][0]; bcur[n][1] = bnext[n][1]; bcur[n][2] = bnext[n][2]; bcur[n][3] = bnext[n][3]; }
+    load_bias(j0 + 32 < Np ? j0 + 32 : 0, bnext);          // next chunk (wraps to chunk 0 for pass 2)
+    scores(j0, bcur, s);
+    float c0 = -FLT_MAX, c1 = -FLT_MAX;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { c0 = fmaxf(c0, fmaxf(s[n][0], s[n][1])); c1 = fmaxf(c1, fmaxf(s[n][2], s[n][3])); }
+    c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1)); c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1)); c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
+    const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);
+    l0 *= exp2f(m0 - n0); l1 *= exp2f(m1 - n1);
+    m0 = n0; m1 = n1;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { l0 += exp2f(s[n][0] - m0) + exp2f(s[n][1] - m0); l1 += exp2f(s[n][2] - m1) + exp2f(s[n][3] - m1); }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+
+  // ---- pass 2: probabilities (written for the pair aggregation) and P V
+  float oacc[5][4];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) oacc[m][0] = oacc[m][1] = oacc[m][2] = oacc[m][3] = 0.f;
+  float* pr0 = probs + (bh * N + i0) * N;
+  float* pr1 = probs + (bh * N + i1) * N;
+  const bool w0 = r0 + g < N, w1 = r0 + g + 8 < N, vec2 = (N % 2) == 0;
+  for (int j0 = 0; j0 < Np; j0 += 32) {
+    float s[4][4], bcur[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { bcur[n][0] = bnext[n][0]; bcur[n][1] = bnext[n][1]; bcur[n][2] = bnext[n][2]; bcur[n][3] = bnext[n][3]; }
+    if (j0 + 32 < Np) load_bias(j0 + 32, bnext);
+    scores(j0, bcur, s);
+    float pacc[5][4];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) pacc[m][0] = pacc[m][1] = pacc[m][2] = pacc[m][3] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float p00 = exp2f(s[n][0] - m0) * inv0, p01 = exp2f(s[n][1] - m0) * inv0;
+      const float p10 = exp2f(s[n][2] - m1) * inv1, p11 = exp2f(s[n][3] - m1) * inv1;
+      const int j = j0 + 8 * n + 2 * t;
+      if (vec2 && j + 1 < N) {
+        if (w0) *reinterpret_cast<float2*>(pr0 + j) = make_float2(p00, p01);
+        if (w1) *reinterpret_cast<float2*>(pr1 + j) = make_float2(p10, p11);
+      } else {
+        if (j < N) { if (w0) pr0[j] = p00; if (w1) pr1[j] = p10; }
+        if (j + 1 < N) { if (w0) pr0[j + 1] = p01; if (w1) pr1[j + 1] = p11; }
+      }
+      uint32_t phi[4], plo[4];                       // A fragment: k-index t <-> key 2t, t+4 <-> key 2t+1
+      split_tf32(p00, phi[0], plo[0]); split_tf32(p10, phi[1], plo[1]);
+      split_tf32(p01, phi[2], plo[2]); split_tf32(p11, phi[3], plo[3]);
+      const float* vr = Vs + (size_t)(j0 + 8 * n + 2 * t) * kVS + g;
+      uint32_t vh0[5], vl0[5], vh1[5], vl1[5];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        split_tf32(vr[8 * m], vh0[m], vl0[m]);
+        split_tf32(vr[kVS + 8 * m], vh1[m], vl1[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < 5; ++m) mma_tf32(pacc[m], phi, vl0[m], vl1[m]);
+#pragma unroll
+      for (int m = 0; m < 5; ++m) mma_tf32(pacc[m], plo, vh0[m], vh1[m]);
+#pragma unroll
+      for (int m = 0; m < 5; ++m) mma_tf32(pacc[m], phi, vh0[m], vh1[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) { oacc[m][0] += pacc[m][0]; oacc[m][1] += pacc[m][1]; oacc[m][2] += pacc[m][2]; oacc[m][3] += pacc[m][3]; }
+  }
+
+  // ---- node features of these 16 rows (as in the SIMT kernel): via a per-warp tile [16][41]
+  float* O = Ot + warp * 16 * (kVD + 1);
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    O[g * (kVD + 1) + 8 * m + 2 * t] = oacc[m][0]; O[g * (kVD + 1) + 8 * m + 2 * t + 1] = oacc[m][1];
+    O[(g + 8) * (kVD + 1) + 8 * m + 2 * t] = oacc[m][2]; O[(g + 8) * (kVD + 1) + 8 * m + 2 * t + 1] = oacc[m][3];
+  }
+  __syncwarp();
+  for (int o = lane; o < 16 * kSv; o += 32) {
+    const int r = o / kSv, c = o % kSv, i = r0 + r;
+    if (i < N) feats[((size_t)b * N + i) * kFeat + h * kSv + c] = O[r * (kVD + 1) + c];      // 'b i h c -> b i (h c)'
+  }
+  for (int o = lane; o < 16 * kPv; o += 32) {
+    const int r = o / kPv, p = o % kPv, i = r0 + r;
+    if (i >= N) continue;
+    const size_t bn = (size_t)b * N + i;
+    float R[9], tr[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = __ldg(rots + bn * 9 + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tr[k] = __ldg(trans + bn * 3 + k);
+    float it[3], gp[3], l[3];                        // invert_rigids (r3.py:54-59) then rigids_apply  folding.py:121
+#pragma unroll
+    for (int k = 0; k < 3; ++k) it[k] = -(R[k] * tr[0] + R[3 + k] * tr[1] + R[6 + k] * tr[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gp[k] = O[r * (kVD + 1) + kSv + 3 * p + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) l[k] = it[k] + (R[k] * gp[0] + R[3 + k] * gp[1] + R[6 + k] * gp[2]);
+    float* f = feats + bn * kFeat;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f[kFeatPt + k * (kH * kPv) + h * kPv + p] = l[k];              // '(r n)'  folding.py:122
+    f[kFeatNorm + h * kPv + p] = sqrtf(l[0] * l[0] + l[1] * l[1] + l[2] * l[2] + 1e-8f);       // :123
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // pair aggregation: o_pair[b,i,h,:] = sum_j a[b,h,i,j] z[b,i,j,:].  One CTA per (b, i): the 12 x N
 // probabilities of the row are staged (transposed to [j][12]) in shared memory, each warp streams
 // every 4th z[i,j,:] row straight from HBM into registers (one 16-byte load per lane covers the 512 B
@@ -450,6 +701,12 @@ static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_fe
   return w;
 }
 
+// ABX_IPA_ATTENTION=simt selects the SIMT attention kernel (A/B measurements); default: tensor-core kernel
+static int attention_impl() {
+  static int v = [] { const char* e = getenv("ABX_IPA_ATTENTION"); return (e && e[0] == 's') ? 1 : 0; }();
+  return v;
+}
+
 static int ipa_features(cudaStream_t s, int B, int N, const float* x, const float* z, const float* mask,
                         const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
                         float* feats, const IpaWorkspace& ws) {
@@ -476,12 +733,21 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
     pair_bias = ws.bias;
   }
 
-  const size_t asmem = attn_smem_bytes(N);
-  ABX_CUDA(cudaFuncSetAttribute(ipa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
-  ipa_attention_kernel<<<dim3(ceil_div(N, kRows), kH, B), kAttnThreads, asmem, s>>>(
-      N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, feats);
-  count_launch();
-  if ((rc = check_launch("ipa_attention_kernel"))) return rc;
+  const size_t msmem = attn_mma_smem_floats(N) * sizeof(float);
+  if (attention_impl() == 0 && msmem <= 227 * 1024) {
+    ABX_CUDA(cudaFuncSetAttribute(ipa_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    ipa_attention_mma_kernel<<<dim3(ceil_div(N, 16 * kMW), kH, B), kMW * 32, msmem, s>>>(
+        N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, feats);
+    count_launch();
+    if ((rc = check_launch("ipa_attention_mma_kernel"))) return rc;
+  } else {
+    const size_t asmem = attn_smem_bytes(N);
+    ABX_CUDA(cudaFuncSetAttribute(ipa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+    ipa_attention_kernel<<<dim3(ceil_div(N, kRows), kH, B), kAttnThreads, asmem, s>>>(
+        N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, feats);
+    count_launch();
+    if ((rc = check_launch("ipa_attention_kernel"))) return rc;
+  }
 
   const size_t gsmem = agg_smem_bytes(N);
   ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));

@@ -340,6 +340,13 @@ def run_b200(a):
             pass
         peak = peaks.get('hbm_gbs', 6650.0)
         alg = S * 4 * (128 * n_res * n_res + 2 * 256 * n_res + 12 * n_res + n_res) + 4 * 838552     # SURVEY §8d, per layer-call
+        traffic = None                                   # dram read+write bytes of one layer-call from the committed ncu capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ipa_traffic.json')))
+            if tr.get('B') == S and tr.get('N') == n_res:
+                traffic = tr['traffic_bytes']
+        except Exception:
+            pass
         ipa_mean = statistics.mean(ipa_ms)
         achieved = alg / (ipa_mean * 1e-3) / 1e9
         line = {
@@ -356,7 +363,7 @@ def run_b200(a):
                          'algorithmic_bytes_per_launch': alg, 'ms_per_launch': ipa_mean, 'launches_timed': len(ipa_ms),
                          'share_of_step': sum(ipa_ms) / ms_instr,
                          'timed_in': 'eager instrumented step after the graph-replayed timed region' if a.cuda_graph else 'timed region',
-                         'traffic': None},
+                         'traffic': traffic},
             'clocks': clock_info,
         }
         if not a.no_cpu_baseline:

@@ -19,6 +19,7 @@ def main():
     ap.add_argument('--N', type=int, default=350)
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--precomputed-bias', type=int, default=1)
+    ap.add_argument('--profile', type=int, default=0)
     a = ap.parse_args()
     from abx_b200.model.folding import InvariantPointAttention
     from abx_b200.utils.weights import load_seeded_
@@ -46,6 +47,15 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
+    if a.profile:
+        from torch.profiler import ProfilerActivity, profile
+        with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                flush.zero_()
+                ipa(x, z, mask, (rots, trans), pair_bias=bias)
+            torch.cuda.synchronize()
+        for e in sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total)[:10]:
+            print(f'{e.self_device_time_total / e.count:9.1f} us x{e.count:3d}  {e.key[:90]}')
     times.sort()
     ms = times[len(times) // 2]
     alg = B * 4 * (128 * N * N + 2 * 256 * N + 12 * N + N) + 4 * 838552
