@@ -187,7 +187,8 @@ constexpr int kMmaMaxWarps = 12;
 template <int D>
 __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) pair_attention_mma_kernel(
     int L, int H, int S, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
-    const float* __restrict__ bias, const float* __restrict__ key_mask, float scale, float* __restrict__ out) {
+    const float* __restrict__ bias, const float* __restrict__ key_mask, const float* __restrict__ gate, float scale,
+    float* __restrict__ out) {
   constexpr int KS = D + 4, D4 = D / 4, NK = D / 8;   // smem row stride, float4 per row, k-steps of Q K^T (= n-tiles of P V)
   extern __shared__ __align__(16) float sm[];
   const int Lpad = (L + 31) & ~31;
@@ -317,28 +318,36 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32, 1) pair_attention_mma_kerne
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  // optional output gating (seqformer.py:296-299): out = sigmoid(gate) * weighted average, gate laid out like q
   const size_t HD = (size_t)H * D;
+  auto store_row = [&](int i, float a0, float a1, int m) {
+    float2 o2 = make_float2(a0, a1);
+    if (gate) {
+      const float2 gv = *reinterpret_cast<const float2*>(gate + (row0 + i) * (size_t)ld + h * D + 8 * m + 2 * t);
+      o2.x *= 1.f / (1.f + expf(-gv.x));
+      o2.y *= 1.f / (1.f + expf(-gv.y));
+    }
+    *reinterpret_cast<float2*>(out + (row0 + i) * HD + h * D + 8 * m + 2 * t) = o2;
+  };
   if (r0 + g < L) {
-    float* o = out + (row0 + r0 + g) * HD + h * D + 2 * t;
 #pragma unroll
-    for (int m = 0; m < NK; ++m) *reinterpret_cast<float2*>(o + 8 * m) = make_float2(oacc[m][0] * inv0, oacc[m][1] * inv0);
+    for (int m = 0; m < NK; ++m) store_row(r0 + g, oacc[m][0] * inv0, oacc[m][1] * inv0, m);
   }
   if (r0 + g + 8 < L) {
-    float* o = out + (row0 + r0 + g + 8) * HD + h * D + 2 * t;
 #pragma unroll
-    for (int m = 0; m < NK; ++m) *reinterpret_cast<float2*>(o + 8 * m) = make_float2(oacc[m][2] * inv1, oacc[m][3] * inv1);
+    for (int m = 0; m < NK; ++m) store_row(r0 + g + 8, oacc[m][2] * inv1, oacc[m][3] * inv1, m);
   }
 }
 
 template <int D>
 static int launch_attention_mma(cudaStream_t st, int B, int S, int L, int H, const float* q, const float* k, const float* v,
-                                int ld, const float* bias, const float* key_mask, float* out) {
+                                int ld, const float* bias, const float* key_mask, const float* gate, float* out) {
   const int Lpad = (L + 31) & ~31;
   const size_t smem = ((size_t)2 * Lpad * (D + 4) + Lpad) * sizeof(float);
   ABX_REQUIRE(smem <= 227 * 1024, "abx_pair_attention: L=%d with head dim %d needs %zu bytes of shared memory (max 232448)", L, D, smem);
   ABX_CUDA(cudaFuncSetAttribute(pair_attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (L + 15) / 16, nz = (tiles + kMmaMaxWarps - 1) / kMmaMaxWarps, warps = (tiles + nz - 1) / nz;
-  pair_attention_mma_kernel<D><<<dim3(H, B * S, nz), warps * 32, smem, st>>>(L, H, S, q, k, v, ld, bias, key_mask,
+  pair_attention_mma_kernel<D><<<dim3(H, B * S, nz), warps * 32, smem, st>>>(L, H, S, q, k, v, ld, bias, key_mask, gate,
                                                                                1.0f / sqrtf((float)D), out);
   count_launch();
   return check_launch("pair_attention_mma_kernel");
@@ -348,9 +357,14 @@ static int launch_attention_mma(cudaStream_t st, int B, int S, int L, int H, con
 
 // impl: 0 = tensor-core kernel (default for D % 8 == 0), 1 = SIMT kernel
 extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, int D, const float* q, const float* k,
-                                       const float* v, int ld, const float* bias, const float* key_mask, float* out) {
+                                       const float* v, int ld, const float* bias, const float* key_mask, const float* gate,
+                                       float* out) {
   using namespace abx;
-  if (impl == 1) return abx_pair_attention(stream, B, S, L, H, D, q, k, v, ld, bias, key_mask, out);
+  if (impl == 1) {
+    ABX_REQUIRE(gate == nullptr, "abx_pair_attention_impl: output gating is only fused in the tensor-core kernel (impl 0)");
+    return abx_pair_attention(stream, B, S, L, H, D, q, k, v, ld, bias, key_mask, out);
+  }
+  ABX_REQUIRE(gate == nullptr || (uintptr_t)gate % 8 == 0, "abx_pair_attention_impl: gate must be 8-byte aligned");
   ABX_REQUIRE(B > 0 && S > 0 && L > 0 && H > 0 && q && k && v && bias && out, "abx_pair_attention: bad shape or null argument");
   ABX_REQUIRE(ld % 4 == 0 && ld >= H * D, "abx_pair_attention: ld must be a multiple of 4 and >= H*D");
   ABX_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 16 == 0),
@@ -358,10 +372,10 @@ extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int
   ABX_REQUIRE((long long)B * S <= 65535, "abx_pair_attention: B*S exceeds 65535");
   cudaStream_t st = (cudaStream_t)stream;
   switch (D) {
-    case 16: return launch_attention_mma<16>(st, B, S, L, H, q, k, v, ld, bias, key_mask, out);
-    case 32: return launch_attention_mma<32>(st, B, S, L, H, q, k, v, ld, bias, key_mask, out);
-    case 48: return launch_attention_mma<48>(st, B, S, L, H, q, k, v, ld, bias, key_mask, out);
-    case 64: return launch_attention_mma<64>(st, B, S, L, H, q, k, v, ld, bias, key_mask, out);
+    case 16: return launch_attention_mma<16>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
+    case 32: return launch_attention_mma<32>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
+    case 48: return launch_attention_mma<48>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
+    case 64: return launch_attention_mma<64>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
   }
   set_error("abx_pair_attention: head dim %d not instantiated (16, 32, 48, 64)", D);
   return ABX_ERR_INVALID;

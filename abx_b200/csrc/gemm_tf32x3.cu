@@ -186,6 +186,29 @@ __device__ __forceinline__ void store_row(const float (&acc)[BN], const Epilogue
   }
 }
 
+// GLU epilogue (act 5): the tile's first BN/2 accumulator columns are projections, the last BN/2 their gates:
+//   y[row, n0/2 + c] = (acc[c] + b[n0+c]) * sigmoid(acc[BN/2+c] + b[n0+BN/2+c]) * row_scale[row]
+// (left/right projections and gates of TriangleMultiplication, seqformer.py:452-460, as one GEMM with the weight
+// rows interleaved per tile); ldy is the leading dimension of the half-width output.
+template <int BN>
+__device__ __forceinline__ void store_row_glu(const float (&acc)[BN], const Epilogue& ep, float* __restrict__ y, int ldy,
+                                              int row, int n0, int Nout) {
+  constexpr int HB = BN / 2;
+  if (n0 >= Nout) return;
+  const float sc = ep.row_scale ? __ldg(ep.row_scale + row) : 1.f;
+  float* yr = y + (size_t)row * ldy + n0 / 2;
+#pragma unroll
+  for (int c = 0; c < HB; c += 4) {
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float pb = ep.bias ? __ldg(ep.bias + n0 + c + u) : 0.f, gb = ep.bias ? __ldg(ep.bias + n0 + HB + c + u) : 0.f;
+      o[u] = (acc[c + u] + pb) * (1.f / (1.f + expf(-(acc[HB + c + u] + gb)))) * sc;
+    }
+    *reinterpret_cast<float4*>(yr + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int BN>
@@ -383,7 +406,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           case 1: store_row<1, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
           case 2: store_row<2, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
           case 3: store_row<3, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
-          default: store_row<4, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
+          case 4: store_row<4, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
+          default: if constexpr (BN == 128) store_row_glu<BN>(acc, ep, yt, ldy, row, n0, Nout); break;
         }
       }
     }
@@ -536,8 +560,14 @@ extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float
   ABX_REQUIRE(abx::gemm_tf32x3_supported(M, Nout, K, x, ldx, w, ldw),
               "abx_gemm_tf32x3: K, ldx, ldw must be multiples of 4 with ldx, ldw >= K, and x, w 16-byte aligned "
               "(K=%d ldx=%d ldw=%d)", K, ldx, ldw);
-  ABX_REQUIRE(ldy >= Nout, "abx_gemm_tf32x3: ldy < Nout");
-  ABX_REQUIRE(act >= 0 && act <= 4 && ((act != 2 && act != 4) || gate), "abx_gemm_tf32x3: bad activation / missing gate");
+  ABX_REQUIRE(act >= 0 && act <= 5 && ((act != 2 && act != 4) || gate), "abx_gemm_tf32x3: bad activation / missing gate");
+  if (act == 5) {
+    ABX_REQUIRE(Nout % 128 == 0 && ldy >= Nout / 2 && ldy % 4 == 0 && (uintptr_t)y % 16 == 0 && !residual && !transpose_n,
+                "abx_gemm_tf32x3: the GLU epilogue needs Nout %% 128 == 0, ldy >= Nout/2 (multiple of 4), aligned y, no residual");
+    tile_n = 128;
+  } else {
+    ABX_REQUIRE(ldy >= Nout, "abx_gemm_tf32x3: ldy < Nout");
+  }
   ABX_REQUIRE(transpose_n >= 0 && (transpose_n == 0 || M % (transpose_n * transpose_n) == 0),
               "abx_gemm_tf32x3: M must be a multiple of transpose_n^2");
   return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, residual, gate, row_scale, act,

@@ -53,6 +53,17 @@ class Attention(nn.Module):
             self._qkv_cache = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
         return self._qkv_cache[1]
 
+    def _qkvg_weight(self):
+        """[Wq; Wk; Wv; Wgate] and the matching bias (zeros for q, k, v) for the fused pair-attention path."""
+        ws = (self.proj_q.weight, self.proj_k.weight, self.proj_v.weight, self.gate.weight, self.gate.bias)
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if getattr(self, '_qkvg_cache', (None,))[0] != key:
+            with torch.no_grad():
+                w = torch.cat([t.detach() for t in ws[:4]], dim=0).contiguous()
+                b = torch.cat([torch.zeros(w.shape[0] - ws[4].shape[0], device=w.device, dtype=w.dtype), ws[4].detach()])
+            self._qkvg_cache = (key, w, b.contiguous())
+        return self._qkvg_cache[1], self._qkvg_cache[2]
+
     def forward(self, q_data, k_data=None, bias=None, k_mask=None, residual=None):
         """q_data [B,S,L,C]; bias [B,H,L,L] (shared over S); k_mask [B,S|1,L] bool.
         `residual` [B,S,L,C] is added in the output projection's epilogue."""
@@ -89,9 +100,9 @@ class Attention(nn.Module):
         attention core without materialised logits (abx_pair_attention), gate and residual in GEMM epilogues.
         `transpose_n`: x is the 'b j i c' view of the pair tensor; output / residual are 'b i j c'."""
         from abx_b200 import ops
-        qkv = ops.linear(x, self._qkv_weight())
-        o = ops.pair_attention(qkv, bias, key_mask, self.num_head)
-        gated = self.gate(x, act='sigmoid_mul', gate=o)
+        w, b = self._qkvg_weight()
+        qkvg = ops.linear(x, w, b)                                            # q | k | v | gate pre-activation in one GEMM
+        gated = ops.pair_attention(qkvg, bias, key_mask, self.num_head, gated=True)   # sigmoid(gate) * attention
         return self.proj_out(gated, residual=residual, transpose_n=transpose_n)
 
 
@@ -159,12 +170,30 @@ class TriangleMultiplication(nn.Module):
         self.outgoing = c.orientation == 'per_row'
         self.config = c
 
+    def _glu_weight(self):
+        """Rows of left_proj / left_gate / right_proj / right_gate interleaved in blocks of 64 so that every
+        128-column GEMM tile holds 64 projection columns followed by their 64 gate columns (GLU epilogue)."""
+        ps = (self.left_proj, self.left_gate, self.right_proj, self.right_gate)
+        key = tuple((p.weight.data_ptr(), p.weight._version, p.bias._version) for p in ps)
+        if getattr(self, '_glu_cache', (None,))[0] != key:
+            with torch.no_grad():
+                ws, bs = [], []
+                for proj, gate in ((ps[0], ps[1]), (ps[2], ps[3])):
+                    for c in range(0, proj.weight.shape[0], 64):
+                        ws += [proj.weight[c:c + 64], gate.weight[c:c + 64]]
+                        bs += [proj.bias[c:c + 64], gate.bias[c:c + 64]]
+                self._glu_cache = (key, torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous())
+        return self._glu_cache[1], self._glu_cache[2]
+
     def forward(self, act, mask, residual=None):
         """seqformer.py:413-504.  Gates, pair mask and the residual ride in GEMM epilogues."""
+        from abx_b200 import ops
         pm = (mask[:, :, None] * mask[:, None, :]).to(act.dtype)
         act = self.norm(act)
-        left = self.left_proj(act, act='gate', gate=self.left_gate(act), row_scale=pm)
-        right = self.right_proj(act, act='gate', gate=self.right_gate(act), row_scale=pm)
+        w, b = self._glu_weight()
+        lr = ops.linear(act, w, b, act='glu', row_scale=pm)      # [left | right] = proj * sigmoid(gate) * mask, one GEMM
+        inter = lr.shape[-1] // 2
+        left, right = lr[..., :inter], lr[..., inter:]
         # channel-major so the triangle product is one batched GEMM per channel
         lt, rt_ = left.permute(0, 3, 1, 2), right.permute(0, 3, 1, 2)                 # b c i k
         if self.outgoing:

@@ -7,7 +7,7 @@ import torch
 
 from abx_b200 import lib
 
-ACT = {None: 0, 'none': 0, 'relu': 1, 'gate': 2, 'sigmoid': 3, 'sigmoid_mul': 4}
+ACT = {None: 0, 'none': 0, 'relu': 1, 'gate': 2, 'sigmoid': 3, 'sigmoid_mul': 4, 'glu': 5}
 
 
 def linear(x, weight, bias=None, act=None, residual=None, gate=None, row_scale=None, out=None, tile_n=0, transpose_n=0):
@@ -30,14 +30,15 @@ def linear(x, weight, bias=None, act=None, residual=None, gate=None, row_scale=N
     w = weight.detach()
     if not w.is_contiguous():
         w = w.contiguous()
-    y = out if out is not None else torch.empty(lead + (Nout,), device=x.device, dtype=torch.float32)
+    n_y = Nout // 2 if act == 'glu' else Nout           # 'glu': projection/gate column pairs collapse (see the header)
+    y = out if out is not None else torch.empty(lead + (n_y,), device=x.device, dtype=torch.float32)
     res = residual.reshape(-1, Nout).contiguous() if residual is not None else None
     g = gate.reshape(-1, Nout).contiguous() if gate is not None else None
     rs = row_scale.reshape(-1).to(torch.float32).contiguous() if row_scale is not None else None
     with lib.device_guard(x2):
         lib.check(L.abx_gemm_tf32x3(lib.stream(), M, Nout, K, lib.ptr_any(x2), ldx, lib.ptr(w, torch.float32), K,
                                     lib.ptr(bias.detach() if bias is not None else None), lib.ptr(res), lib.ptr(g),
-                                    lib.ptr(rs), ACT[act], transpose_n, lib.ptr(y), Nout, tile_n))
+                                    lib.ptr(rs), ACT[act], transpose_n, lib.ptr(y), n_y, tile_n))
     return y
 
 
@@ -59,13 +60,14 @@ def layer_norm(x, weight, bias, eps=1e-5, transpose_n=0):
     return y
 
 
-def pair_attention(qkv, bias, key_mask, num_head, impl='mma'):
-    """Fused attention core for TriangleAttention.  qkv [B,S,L,3*H*D] (q | k | v slices of one projection),
-    bias [B,H,L,L], key_mask [B,L] (bool/float, None = keep all)  ->  [B,S,L,H*D].
+def pair_attention(qkv, bias, key_mask, num_head, impl='mma', gated=False):
+    """Fused attention core for TriangleAttention.  qkv [B,S,L,3*H*D] (q | k | v slices of one projection;
+    with `gated=True` [B,S,L,4*H*D] = q | k | v | gate pre-activation), bias [B,H,L,L], key_mask [B,L]
+    (bool/float, None = keep all)  ->  [B,S,L,H*D] (times sigmoid(gate) when gated).
     impl: 'mma' (tensor cores, 3xTF32) or 'simt'."""
     L_ = lib.load()
-    B, S, L, C3 = qkv.shape
-    HD = C3 // 3
+    B, S, L, Cw = qkv.shape
+    HD = Cw // (4 if gated else 3)
     D = HD // num_head
     assert qkv.is_contiguous() and qkv.dtype == torch.float32
     bias = bias.float().contiguous()
@@ -74,6 +76,6 @@ def pair_attention(qkv, bias, key_mask, num_head, impl='mma'):
     base, esz = qkv.data_ptr(), 4
     with lib.device_guard(qkv):
         lib.check(L_.abx_pair_attention_impl(lib.stream(), {'mma': 0, 'simt': 1}[impl], B, S, L, num_head, D, base,
-                                             base + HD * esz, base + 2 * HD * esz, C3,
-                                        lib.ptr(bias), lib.ptr(km), lib.ptr(out)))
+                                             base + HD * esz, base + 2 * HD * esz, Cw,
+                                             lib.ptr(bias), lib.ptr(km), (base + 3 * HD * esz) if gated else None, lib.ptr(out)))
     return out

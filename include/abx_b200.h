@@ -118,7 +118,9 @@ int abx_linear_f32(void* stream, int M, int Nout, int K, const float* x, int ldx
  * D = A_hi W_lo + A_lo W_hi + A_hi W_hi is accumulated in fp32 (3xTF32).  Used for the node GEMMs of IPA
  * (folding.py:69-86,130-132), IpaScore (score_network.py:117-137) and the trunk's dense layers
  * (seqformer.py).   w [Nout, ldw] row-major (nn.Linear layout when ldw == K).
- *   v = acc + bias;  act: 0 none, 1 relu(v), 2 v * sigmoid(gate), 3 sigmoid(v), 4 sigmoid(v) * gate
+ *   v = acc + bias;  act: 0 none, 1 relu(v), 2 v * sigmoid(gate), 3 sigmoid(v), 4 sigmoid(v) * gate,
+ *   5 GLU: per 128-column tile the first 64 columns are projections and the last 64 their gates,
+ *     y[:, n0/2 + c] = v[n0+c] * sigmoid(v[n0+64+c]) (y has Nout/2 columns; seqformer.py:452-460 as one GEMM)
  *   (gate [M,ldy]);  then y = v * row_scale[row] + residual   (row_scale [M], residual [M,ldy]; all optional)
  *   — the gated projections, masked projections and residual adds of seqformer.py fused into the GEMM
  *   transpose_n = n > 0: the M rows are (b,i,j) of a [B,n,n,*] tensor and row (b,i,j) of the result is stored
@@ -148,9 +150,12 @@ int abx_layernorm(void* stream, long long rows, int C, const float* x, const flo
 int abx_pair_attention(void* stream, int B, int S, int L, int H, int D, const float* q, const float* k,
                        const float* v, int ld, const float* bias, const float* key_mask, float* out);
 /* Same operation with a choice of implementation: impl 0 = tensor-core kernel (mma.sync m16n8k8 TF32 with the
- * 3xTF32 operand split, FlashAttention-2 dataflow in registers), impl 1 = the SIMT kernel above. */
+ * 3xTF32 operand split, FlashAttention-2 dataflow in registers), impl 1 = the SIMT kernel above.
+ * gate (impl 0 only, may be NULL): pre-activation of the output gate laid out like q (row stride ld);
+ * out = sigmoid(gate) * attention  (seqformer.py:296-299) — with q|k|v|gate produced by one GEMM. */
 int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, int D, const float* q, const float* k,
-                            const float* v, int ld, const float* bias, const float* key_mask, float* out);
+                            const float* v, int ld, const float* bias, const float* key_mask, const float* gate,
+                            float* out);
 
 /* Which GEMM the IPA pipeline uses for its node layers: 0 auto (tcgen05 when operands qualify),
  * 1 SIMT (abx_linear_f32), 2 tcgen05 only.  Process-wide; meant for A/B measurements and tests. */

@@ -56,3 +56,15 @@ def test_gemm_rejects_bad_arguments(cuda_device):
         ops.linear(torch.zeros(4, 6, device='cuda'), torch.zeros(3, 6, device='cuda'))     # K % 4 != 0
     with pytest.raises(lib.AbxError):
         ops.linear(torch.zeros(4, 8), torch.zeros(3, 8))                                   # CPU tensors
+
+
+def test_gemm_glu_epilogue(cuda_device):
+    """act 'glu': 128-column tiles of [64 projections | 64 gates] -> proj * sigmoid(gate) * row_scale."""
+    from abx_b200 import ops
+    m, k = 333, 192
+    x, w, b, rs = np_randn(40, m, k).cuda(), np_randn(41, 512, k).cuda(), np_randn(42, 512).cuda(), np_randn(43, m).cuda()
+    y = ops.linear(x, w, b, act='glu', row_scale=rs)
+    lin = torch.nn.functional.linear(x.double(), w.double(), b.double()).reshape(m, 4, 2, 64)
+    ref = (lin[:, :, 0] * torch.sigmoid(lin[:, :, 1])).reshape(m, 256) * rs.double()[:, None]
+    assert y.shape == (m, 256)
+    assert maxabs(y.cpu(), ref.cpu()) < 3e-6 * float(ref.abs().max())

@@ -83,3 +83,15 @@ def test_gemm_transposed_store(cuda_device):
     assert maxabs(y.cpu(), (lin.transpose(1, 2) + res.double()).cpu()) < 3e-6 * float(lin.abs().max())
     y = ops.linear(x, w, b, act='sigmoid_mul', gate=gate, transpose_n=n)
     assert maxabs(y.cpu(), (torch.sigmoid(lin) * gate.double()).transpose(1, 2).cpu()) < 3e-6 * float(gate.abs().max())
+
+
+def test_pair_attention_fused_output_gate(cuda_device):
+    from abx_b200 import ops
+    B, S, L, H, D = 1, 3, 70, 4, 48
+    qkvg = np_randn(30, B, S, L, 4 * H * D).cuda()
+    bias = np_randn(31, B, H, L, L).cuda()
+    mask = torch.ones(B, L, dtype=torch.bool).cuda()
+    out = ops.pair_attention(qkvg, bias, mask, H, gated=True)
+    qkv = qkvg[..., :3 * H * D].contiguous()
+    ref = _attention_reference(qkv, bias, mask, H) * torch.sigmoid(qkvg[..., 3 * H * D:].double())
+    assert maxabs(out.cpu(), ref.cpu()) < 3e-6 * max(1.0, float(ref.abs().max()))
