@@ -121,6 +121,16 @@ struct Epilogue {
   int act;                 // 0 none, 1 relu, 2 v * sigmoid(gate), 3 sigmoid(v), 4 sigmoid(v) * gate
   int transpose_n;         // n > 0: rows are (b,i,j) of a [B,n,n,*] tensor and row (b,i,j) is stored to (b,j,i);
                            // y and residual use the transposed row, gate / row_scale the GEMM's own row
+  int cm_n, cm_np;         // GLU only, cm_n = n > 0: rows are (b,i,k) of a [B,n,n,*] tensor and output channel c of row
+                           // (b,i,k) goes to y[b][c][i][k] with rows of cm_np >= n floats (channel-major operands of
+                           // the triangle-multiplication product)
+};
+
+// Batched "NT" product mode of the kernel (triangle multiplication, seqformer.py:470-500): problem bc of `batches`
+// multiplies rows [base(bc), base(bc)+rows) of the A and B operand maps; base(bc) = (bc / inner) * outer_rows +
+// (bc % inner) * rows.  Output tile rows/cols are local to the problem: y[bc][i][j], leading dimension ldy.
+struct Batched {
+  int batches, rows, inner, outer_rows;
 };
 
 template <int ACT>
@@ -196,6 +206,18 @@ __device__ __forceinline__ void store_row_glu(const float (&acc)[BN], const Epil
   constexpr int HB = BN / 2;
   if (n0 >= Nout) return;
   const float sc = ep.row_scale ? __ldg(ep.row_scale + row) : 1.f;
+  if (ep.cm_n > 0) {                                // channel-major store: lanes = consecutive k -> coalesced per channel
+    const long long n = ep.cm_n, nn = n * n, b = row / nn, r = row % nn, i = r / n, k = r % n;
+    const long long C2 = Nout / 2;
+    float* yc = y + (((b * C2 + n0 / 2) * n + i) * ep.cm_np + k);
+    const long long cstride = n * ep.cm_np;
+#pragma unroll
+    for (int c = 0; c < HB; ++c) {
+      const float pb = ep.bias ? __ldg(ep.bias + n0 + c) : 0.f, gb = ep.bias ? __ldg(ep.bias + n0 + HB + c) : 0.f;
+      yc[c * cstride] = (acc[c] + pb) * (1.f / (1.f + expf(-(acc[HB + c] + gb)))) * sc;
+    }
+    return;
+  }
   float* yr = y + (size_t)row * ldy + n0 / 2;
 #pragma unroll
   for (int c = 0; c < HB; c += 4) {
@@ -215,7 +237,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
                    int Nout, int K, Epilogue ep, float* __restrict__ y, int ldy, int trust_trunc, int kb_per_drain,
-                   int splits, long long split_stride) {
+                   int splits, long long split_stride, Batched bt) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -237,8 +259,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   // raw partial product to y + s split_stride (the caller reduces); splits == 1 is the plain GEMM
   const int nkb_total = (K + kBK - 1) / kBK;
   const int kbs = (nkb_total + splits - 1) / splits;
+  // batched mode: M and Nout are the per-problem sizes (bt.rows), the tile index also runs over the problems
   const int nt = (Nout + BN - 1) / BN, mt = (M + kBM - 1) / kBM;
-  const int mnt = nt * mt, tiles = mnt * splits;
+  const int mnt = nt * mt * (bt.batches > 0 ? bt.batches : 1), tiles = mnt * splits;
+  auto batch_base = [&](int bc) { return (bc / bt.inner) * bt.outer_rows + (bc % bt.inner) * bt.rows; };
   auto tile_nkb = [&](int tile) { const int k0 = (tile / mnt) * kbs; return min(kbs, nkb_total - k0); };
 
   if (warp == 0 && lane == 0) {
@@ -276,7 +300,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int rem = tile % mnt, kb0 = (tile / mnt) * kbs, nkb = tile_nkb(tile);
-        const int m0 = (rem / nt) * kBM, n0 = (rem % nt) * BN;
+        int m0 = ((rem / nt) % mt) * kBM, n0 = (rem % nt) * BN;
+        if (bt.batches > 0) { const int base = batch_base(rem / (nt * mt)); m0 += base; n0 += base; }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -371,8 +396,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint32_t lit = 0;                                // k-slabs this WG has drained (its own phase counter)
     for (int tile = blockIdx.x + g * gridDim.x; tile < tiles; tile += 2 * gridDim.x) {
       const int rem = tile % mnt, nkb = tile_nkb(tile);
-      const int m0 = (rem / nt) * kBM, n0 = (rem % nt) * BN;
-      float* __restrict__ yt = y + (long long)(tile / mnt) * split_stride;
+      const int m0 = ((rem / nt) % mt) * kBM, n0 = (rem % nt) * BN;
+      float* __restrict__ yt = y + (long long)(tile / mnt) * split_stride +
+                               (bt.batches > 0 ? (long long)(rem / (nt * mt)) * bt.rows * ldy : 0);
       const int row = m0 + 32 * q + lane;
       if (row < M) {                                 // pull this row's gate / residual pieces into L2 ahead of the epilogue
         const int ncol = min(BN, Nout - n0);
@@ -486,21 +512,22 @@ int kb_per_drain() {
 
 template <int BN>
 int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw, const Epilogue& ep,
-              float* y, int ldy, int splits = 1, long long split_stride = 0) {
+              float* y, int ldy, int splits = 1, long long split_stride = 0, Batched bt = Batched{0, 0, 1, 0},
+              int map_rows_a = 0, int map_rows_b = 0) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ma, mb;
   int rc;
-  if ((rc = make_map(&ma, x, M, K, ldx, kBM))) return rc;
-  if ((rc = make_map(&mb, w, Nout, K, ldw, BN))) return rc;
+  if ((rc = make_map(&ma, x, map_rows_a ? map_rows_a : M, K, ldx, kBM))) return rc;
+  if ((rc = make_map(&mb, w, map_rows_b ? map_rows_b : Nout, K, ldw, BN))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     ABX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ceil_div(Nout, BN) * ceil_div(M, kBM) * splits;
+  const int tiles = ceil_div(Nout, BN) * ceil_div(M, kBM) * splits * (bt.batches > 0 ? bt.batches : 1);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tf32x3_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(ma, mb, M, Nout, K, ep, y, ldy, trust_trunc(), kb_per_drain(),
-                                                                 splits, split_stride);
+                                                                 splits, split_stride, bt);
   count_launch();
   return check_launch("gemm_tf32x3_kernel");
 }
@@ -515,8 +542,8 @@ bool gemm_tf32x3_supported(int M, int Nout, int K, const float* x, int ldx, cons
 // act: see Epilogue.  tile_n: 0 = choose, else 32/64/128.
 int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                        const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
-                       int transpose_n, float* y, int ldy, int tile_n) {
-  Epilogue ep{bias, residual, gate, row_scale, act, transpose_n};
+                       int transpose_n, float* y, int ldy, int tile_n, int cm_n = 0, int cm_np = 0) {
+  Epilogue ep{bias, residual, gate, row_scale, act, transpose_n, cm_n, cm_np};
   if (tile_n == 0) {
     // enough CTAs to cover the 148 SMs beats wide tiles for the small-M node GEMMs
     const int mt = ceil_div(M, kBM);
@@ -542,7 +569,7 @@ int launch_gemm_tf32x3_splitk(cudaStream_t s, int M, int Nout, int K, const floa
   if (splits > nkb) splits = nkb;
   while (splits > 1 && (splits - 1) * ceil_div(nkb, splits) >= nkb) --splits;   // no empty split
   *splits_io = splits;
-  Epilogue ep{nullptr, nullptr, nullptr, nullptr, 0, 0};
+  Epilogue ep{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
   const long long stride = (long long)M * Nout;
   switch (tile_n) {
     case 32: return launch_bn<32>(s, M, Nout, K, x, ldx, w, ldw, ep, partials, Nout, splits, stride);
@@ -551,7 +578,26 @@ int launch_gemm_tf32x3_splitk(cudaStream_t s, int M, int Nout, int K, const floa
   }
 }
 
+// out[bc][i][j] = sum_k a[bc][i][k] b[bc][j][k] for bc < batches; a / b rows of problem bc start at row
+// (bc / inner) * outer_rows + (bc % inner) * n of their [*, kpad] matrices (kpad >= n, zero padded), out [batches][n][ldo].
+int launch_gemm_tf32x3_batched_nt(cudaStream_t s, int batches, int n, int kpad, int inner, int outer_rows, int total_rows,
+                                  const float* a, const float* b, float* out, int ldo) {
+  Epilogue ep{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+  Batched bt{batches, n, inner, outer_rows};
+  return launch_bn<128>(s, n, n, kpad, a, kpad, b, kpad, ep, out, ldo, 1, 0, bt, total_rows, total_rows);
+}
+
 }  // namespace abx
+
+extern "C" int abx_gemm_tf32x3_batched_nt(void* stream, int batches, int n, int kpad, int inner, int outer_rows, int total_rows,
+                                          const float* a, const float* b, float* out, int ldo) {
+  ABX_REQUIRE(batches > 0 && n > 0 && a && b && out, "abx_gemm_tf32x3_batched_nt: bad shape or null argument");
+  ABX_REQUIRE(kpad % 4 == 0 && kpad >= n && ldo % 4 == 0 && ldo >= n && inner > 0,
+              "abx_gemm_tf32x3_batched_nt: kpad and ldo must be multiples of 4 and >= n");
+  ABX_REQUIRE(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)out % 16 == 0),
+              "abx_gemm_tf32x3_batched_nt: operands must be 16-byte aligned");
+  return abx::launch_gemm_tf32x3_batched_nt((cudaStream_t)stream, batches, n, kpad, inner, outer_rows, total_rows, a, b, out, ldo);
+}
 
 extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                                const float* bias, const float* residual, const float* gate, const float* row_scale,
@@ -572,4 +618,13 @@ extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float
               "abx_gemm_tf32x3: M must be a multiple of transpose_n^2");
   return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, residual, gate, row_scale, act,
                                  transpose_n, y, ldy, tile_n);
+}
+
+extern "C" int abx_gemm_tf32x3_glu_cm(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                                      const float* bias, const float* row_scale, int n, int np, float* y) {
+  ABX_REQUIRE(M > 0 && Nout > 0 && K > 0 && x && w && y, "abx_gemm_tf32x3_glu_cm: bad shape or null argument");
+  ABX_REQUIRE(abx::gemm_tf32x3_supported(M, Nout, K, x, ldx, w, ldw), "abx_gemm_tf32x3_glu_cm: unsupported operand layout");
+  ABX_REQUIRE(Nout % 128 == 0 && n > 0 && np >= n && M % (n * n) == 0, "abx_gemm_tf32x3_glu_cm: Nout %% 128, M %% n^2 and np >= n required");
+  return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, nullptr, nullptr, row_scale, 5, 0, y,
+                                 Nout / 2, 128, n, np);
 }

@@ -65,7 +65,52 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
   }
 }
 
+// LayerNorm over the channels of a CHANNEL-MAJOR tensor x [B, C, n, np] (np >= n: padded rows), written row-major
+// y [B, n, n, C]: the 'b c i j -> b i j c' rearrange + final LayerNorm after the triangle-multiplication product
+// (seqformer.py:500-502).  One CTA per (b, i, 32 values of j): coalesced 128-byte reads along j, transpose
+// through shared memory, warp reductions over the C <= 128 channels, coalesced writes along c.
+__global__ void __launch_bounds__(128) layernorm_cm_kernel(int C, int n, int np, const float* __restrict__ x,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float eps, float* __restrict__ y) {
+  __shared__ float t[128][33];
+  const int j0 = blockIdx.x * 32, i = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < C; c += 4) {
+    const int j = j0 + lane;
+    t[c][lane] = (j < n) ? x[(((size_t)b * C + c) * n + i) * np + j] : 0.f;
+  }
+  __syncthreads();
+  const int nc = C / 32;                         // channels per lane
+  for (int jj = 0; jj < 8; ++jj) {
+    const int jl = warp * 8 + jj, j = j0 + jl;
+    if (j >= n) break;
+    float v[4], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = (k < nc) ? t[lane + 32 * k][jl] : 0.f; sum += v[k]; }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < nc) { const float d = v[k] - mean; sq += d * d; }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    float* yr = y + (((size_t)b * n + i) * n + j) * C;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nc) { const int c = lane + 32 * k; yr[c] = (v[k] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c); }
+  }
+}
+
 }  // namespace abx
+
+extern "C" int abx_layernorm_cm(void* stream, int B, int C, int n, int np, const float* x, const float* gamma,
+                                const float* beta, float eps, float* y) {
+  using namespace abx;
+  ABX_REQUIRE(B > 0 && n > 0 && np >= n && x && gamma && beta && y, "abx_layernorm_cm: bad shape or null argument");
+  ABX_REQUIRE(C % 32 == 0 && C <= 128, "abx_layernorm_cm: C must be a multiple of 32 and <= 128 (got %d)", C);
+  ABX_REQUIRE(n <= 65535 && B <= 65535, "abx_layernorm_cm: n and B must be <= 65535");
+  layernorm_cm_kernel<<<dim3((n + 31) / 32, n, B), 128, 0, (cudaStream_t)stream>>>(C, n, np, x, gamma, beta, eps, y);
+  count_launch();
+  return check_launch("layernorm_cm_kernel");
+}
 
 extern "C" int abx_layernorm(void* stream, long long rows, int C, const float* x, const float* gamma, const float* beta,
                              float eps, int transpose_n, float* y) {

@@ -189,19 +189,13 @@ class TriangleMultiplication(nn.Module):
         """seqformer.py:413-504.  Gates, pair mask and the residual ride in GEMM epilogues."""
         from abx_b200 import ops
         pm = (mask[:, :, None] * mask[:, None, :]).to(act.dtype)
-        act = self.norm(act)
+        n = act.shape[1]
+        x = self.norm(act)
+        # outgoing: sum_k l[i,k] r[j,k]; incoming: sum_k l[k,i] r[k,j] = the same product on the transposed LN output
+        xt = x if self.outgoing else self.norm(act, transpose_n=n)
         w, b = self._glu_weight()
-        lr = ops.linear(act, w, b, act='glu', row_scale=pm)      # [left | right] = proj * sigmoid(gate) * mask, one GEMM
-        inter = lr.shape[-1] // 2
-        left, right = lr[..., :inter], lr[..., inter:]
-        # channel-major so the triangle product is one batched GEMM per channel
-        lt, rt_ = left.permute(0, 3, 1, 2), right.permute(0, 3, 1, 2)                 # b c i k
-        if self.outgoing:
-            out = torch.matmul(lt, rt_.transpose(-1, -2))                            # sum_k l[i,k] r[j,k]
-        else:
-            out = torch.matmul(lt.transpose(-1, -2), rt_)                            # sum_k l[k,i] r[k,j]
-        return self.proj_out(self.final_norm(out.permute(0, 2, 3, 1)), act='gate', gate=self.final_gate(act),
-                             residual=residual)
+        prod = ops.triangle_product(xt, w, b, pm, self.final_norm.weight, self.final_norm.bias, self.final_norm.eps)
+        return self.proj_out(prod, act='gate', gate=self.final_gate(x), residual=residual)
 
 
 class TriangleAttention(nn.Module):

@@ -79,3 +79,45 @@ def pair_attention(qkv, bias, key_mask, num_head, impl='mma', gated=False):
                                              base + HD * esz, base + 2 * HD * esz, Cw,
                                              lib.ptr(bias), lib.ptr(km), (base + 3 * HD * esz) if gated else None, lib.ptr(out)))
     return out
+
+
+_CM_BUFFERS = {}
+
+
+def _cm_buffer(tag, shape, device):
+    """Zero-initialised channel-major scratch buffer, cached per (tag, shape, device): its pad columns are never
+    written, so they stay zero across calls."""
+    key = (tag, tuple(shape), str(device))
+    buf = _CM_BUFFERS.get(key)
+    if buf is None:
+        buf = torch.zeros(shape, device=device, dtype=torch.float32)
+        _CM_BUFFERS[key] = buf
+    return buf
+
+
+def triangle_product(x, w_glu, b_glu, pair_mask, norm_weight, norm_bias, eps=1e-5):
+    """sum_k left[i,k] * right[j,k] per channel + final LayerNorm for TriangleMultiplication (seqformer.py:452-502).
+    x [B,n,n,Cin] = LN(pair) (pass the 'b j i c' transposed LN output for the incoming orientation); w_glu / b_glu:
+    the tile-interleaved [left | right] x [proj | gate] weights (see TriangleMultiplication._glu_weight);
+    pair_mask [B,n,n].  Returns LN(product) as [B,n,n,C] row-major."""
+    L_ = lib.load()
+    B, n, _, K = x.shape
+    Nout = w_glu.shape[0]
+    C = Nout // 4                              # channels of left (= of right)
+    npad = (n + 3) // 4 * 4
+    xc = x if x.is_contiguous() else x.contiguous()
+    lr = _cm_buffer('lr', (B, 2 * C, n, npad), x.device)
+    prod = _cm_buffer('prod', (B, C, n, npad), x.device)
+    rs = pair_mask.reshape(-1).to(torch.float32).contiguous()
+    out = torch.empty(B, n, n, C, device=x.device, dtype=torch.float32)
+    with lib.device_guard(xc):
+        st = lib.stream()
+        lib.check(L_.abx_gemm_tf32x3_glu_cm(st, B * n * n, Nout, K, lib.ptr(xc), K, lib.ptr(w_glu), K, lib.ptr(b_glu), lib.ptr(rs),
+                                            n, npad, lib.ptr(lr)))
+        a_ptr = lr.data_ptr()
+        b_ptr = a_ptr + C * n * npad * 4        # right channels follow the left ones inside each batch element
+        lib.check(L_.abx_gemm_tf32x3_batched_nt(st, B * C, n, npad, C, 2 * C * n, B * 2 * C * n - C * n, a_ptr, b_ptr,
+                                                lib.ptr(prod), npad))
+        lib.check(L_.abx_layernorm_cm(st, B, C, n, npad, lib.ptr(prod), lib.ptr(norm_weight.detach()), lib.ptr(norm_bias.detach()),
+                                      float(eps), lib.ptr(out)))
+    return out

@@ -132,6 +132,21 @@ int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ld
                     const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
                     int transpose_n, float* y, int ldy, int tile_n);
 
+/* Triangle multiplication (seqformer.py:413-504) on the tensor cores, three calls:
+ * (1) abx_gemm_tf32x3_glu_cm: the left/right projections and gates of LN(pair) as ONE GEMM with the GLU epilogue
+ *     (act 5), mask row scale, and the result stored channel-major y [B, Nout/2, n, np] (rows padded to np floats,
+ *     pad columns must be zero: the caller zero-fills the buffer once) — the K-major operands of the product;
+ * (2) abx_gemm_tf32x3_batched_nt: out[bc][i][j] = sum_k a[bc][i][k] b[bc][j][k] for the B*C channel problems
+ *     (row base of problem bc = (bc / inner) * outer_rows + (bc % inner) * n in the [total_rows, kpad] matrices);
+ * (3) abx_layernorm_cm: 'b c i j -> b i j c' + final LayerNorm, then the gated output projection is a GEMM.
+ * The incoming orientation uses the same calls on the transposed LN output (abx_layernorm transpose_n). */
+int abx_gemm_tf32x3_glu_cm(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                           const float* bias, const float* row_scale, int n, int np, float* y);
+int abx_gemm_tf32x3_batched_nt(void* stream, int batches, int n, int kpad, int inner, int outer_rows, int total_rows,
+                               const float* a, const float* b, float* out, int ldo);
+int abx_layernorm_cm(void* stream, int B, int C, int n, int np, const float* x, const float* gamma, const float* beta,
+                     float eps, float* y);
+
 /* ---- LayerNorm ------------------------------------------------------------------------------- */
 /* y = (x - mean) / sqrt(var + eps) * gamma + beta over the last dimension (torch.nn.LayerNorm; every
  * LayerNorm of abx/model/seqformer.py, score_network.py:117-135).  x, y [rows, C] contiguous, C % 4 == 0,

@@ -95,3 +95,34 @@ def test_pair_attention_fused_output_gate(cuda_device):
     qkv = qkvg[..., :3 * H * D].contiguous()
     ref = _attention_reference(qkv, bias, mask, H) * torch.sigmoid(qkvg[..., 3 * H * D:].double())
     assert maxabs(out.cpu(), ref.cpu()) < 3e-6 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('n', [21, 350])
+def test_triangle_product_matches_einsum(cuda_device, n):
+    """GLU GEMM (channel-major store) + batched NT product + channel-major LayerNorm == the reference chain
+    proj*sigmoid(gate)*mask -> einsum('bikc,bjkc->bijc') -> LayerNorm  (seqformer.py:452-502, outgoing)."""
+    from abx_b200 import ops
+    B, K, C = 2 if n < 100 else 1, 192, 128
+    x = np_randn(50, B, n, n, K).cuda()
+    wl, wlg, wr, wrg = (np_randn(51 + i, C, K).cuda() / K ** 0.5 for i in range(4))
+    bl, blg, br, brg = (np_randn(55 + i, C).cuda() * 0.1 for i in range(4))
+    g, be = np_randn(60, C).cuda(), np_randn(61, C).cuda()
+    mask = torch.ones(B, n, device='cuda')
+    mask[0, -3:] = 0
+    pm = mask[:, :, None] * mask[:, None, :]
+    ws, bs = [], []
+    for (pw, pb), (gw, gb) in (((wl, bl), (wlg, blg)), ((wr, br), (wrg, brg))):
+        for c in range(0, C, 64):
+            ws += [pw[c:c + 64], gw[c:c + 64]]
+            bs += [pb[c:c + 64], gb[c:c + 64]]
+    out = ops.triangle_product(x, torch.cat(ws).contiguous(), torch.cat(bs).contiguous(), pm, g, be)
+    xd = x.double()
+    F = torch.nn.functional
+    left = F.linear(xd, wl.double(), bl.double()) * torch.sigmoid(F.linear(xd, wlg.double(), blg.double())) * pm.double()[..., None]
+    right = F.linear(xd, wr.double(), br.double()) * torch.sigmoid(F.linear(xd, wrg.double(), brg.double())) * pm.double()[..., None]
+    ref = F.layer_norm(torch.einsum('bikc,bjkc->bijc', left, right), (C,), g.double(), be.double(), 1e-5)
+    assert out.shape == (B, n, n, C)
+    assert maxabs(out.cpu(), ref.cpu()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    # second call reuses the cached channel-major buffers (pad columns must still be zero)
+    out2 = ops.triangle_product(x, torch.cat(ws).contiguous(), torch.cat(bs).contiguous(), pm, g, be)
+    assert torch.equal(out, out2)
