@@ -29,7 +29,14 @@ namespace abx {
 
 namespace {
 
-constexpr int kBM = 128, kBK = 32;             // 32 fp32 = one 128-byte swizzle row
+#ifndef ABX_GEMM_BK
+#define ABX_GEMM_BK 32
+#endif
+// k-slab width: 32 fp32 = one 128-byte swizzle row, or 16 fp32 = one 64-byte swizzle row (twice the pipeline depth
+// in the same shared memory: the TMA -> convert -> MMA -> commit round trip, not bandwidth, paces the main loop)
+constexpr int kBM = 128, kBK = ABX_GEMM_BK;
+static_assert(kBK == 32 || kBK == 16, "k-slab must be 16 or 32 floats");
+constexpr int kDrainDefault = 32 / kBK;         // register accumulation once per 32 columns of K by default
 constexpr int kThreads = 512, kConvThreads = 128, kAccThreads = 128;
 constexpr int kRegsCtl = 40, kRegsConv = 72, kRegsAcc = 184;   // 128*(40+72) + 256*184 <= 65536
 constexpr uint32_t kTileABytes = kBM * kBK * 4;
@@ -37,9 +44,9 @@ constexpr uint32_t kTileABytes = kBM * kBK * 4;
 template <int BN> struct GemmCfg {
   static constexpr uint32_t kTileBBytes = BN * kBK * 4;
   static constexpr uint32_t kStageBytes = 2 * (kTileABytes + kTileBBytes);     // raw/hi + lo for A and B
-  static constexpr int kStages = BN >= 128 ? 3 : (BN >= 64 ? 4 : 5);
+  static constexpr int kStages = (BN >= 128 ? 3 : (BN >= 64 ? 4 : 5)) * (32 / kBK);
   static constexpr uint32_t kTmemCols = 4 * BN;                                // two partial-sum buffers per accumulator WG
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 512 /* barriers */;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,9 +84,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * kBK * 4) >> 4) << 32;     // SBO: 8 rows of kBK floats (1024 B / 512 B)
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(kBK == 32 ? 2 : 4) << 61;      // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
@@ -306,6 +313,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(empty + s, ph ^ 1);
+          if (trust_trunc & 16) { mbar_arrive(full + s); continue; }      // timing probe: no TMA at all
           mbar_expect_tx(full + s, kTileABytes + Cfg::kTileBBytes);
           tma_load_2d(stage_a(s), &map_a, full + s, (kb0 + kb) * kBK, m0);
           tma_load_2d(stage_b(s), &map_b, full + s, (kb0 + kb) * kBK, n0);
@@ -474,7 +482,7 @@ int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int b
   cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, kBK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ABX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for a [%d,%d] ld=%d operand", (int)r, rows, K, ld);
   return ABX_OK;
@@ -496,8 +504,8 @@ int sm_count() {
 int trust_trunc() {
   static int v = [] {
     const char* e = getenv("ABX_GEMM_TRUST_TRUNC");
-    const char* d = getenv("ABX_GEMM_DEBUG_SKIP");      // timing experiments only: 2 skip split, 4 skip MMA, 8 skip drain
-    return ((e && e[0] == '0') ? 0 : 1) | (d ? (atoi(d) & 14) : 0);
+    const char* d = getenv("ABX_GEMM_DEBUG_SKIP");      // timing experiments only: 2 skip split, 4 skip MMA, 8 skip drain, 16 skip TMA
+    return ((e && e[0] == '0') ? 0 : 1) | (d ? (atoi(d) & 30) : 0);
   }();
   return v;
 }
@@ -506,7 +514,7 @@ int trust_trunc() {
 // core's truncating accumulator never chains more than 12 MMAs), larger values trade a little rounding bias for
 // fewer TMEM reads.  ABX_GEMM_KB_PER_DRAIN overrides the default.
 int kb_per_drain() {
-  static int v = [] { const char* e = getenv("ABX_GEMM_KB_PER_DRAIN"); int n = e ? atoi(e) : 1; return n < 1 ? 1 : (n > 64 ? 64 : n); }();
+  static int v = [] { const char* e = getenv("ABX_GEMM_KB_PER_DRAIN"); int n = e ? atoi(e) : kDrainDefault; return n < 1 ? 1 : (n > 64 ? 64 : n); }();
   return v;
 }
 
