@@ -277,12 +277,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(conv + s, kConvThreads);
+      mbar_init(conv + s, kConvThreads / 32);      // one arrival per converter warp
       mbar_init(empty + s, 1);
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(acc_ready + b, 1);
-      mbar_init(acc_free + b, kAccThreads);
+      mbar_init(acc_free + b, kAccThreads / 32);   // one arrival per accumulator warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -369,7 +369,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(full + s, ph);
-        if (trust_trunc & 2) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); mbar_arrive(conv + s); continue; }
+        if (trust_trunc & 2) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); __syncwarp(); if (lane == 0) mbar_arrive(conv + s); continue; }
         auto split = [&](float4* hi_p, float4* lo_p, int i) {
           float4 v = hi_p[i], h, l;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
@@ -389,7 +389,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll 8
         for (int i = ct; i < (int)(Cfg::kTileBBytes / 16); i += kConvThreads) split(b, blo, i);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(conv + s);
+        __syncwarp();                               // every lane's lo-tile writes are fenced before the warp's single arrival
+        if (lane == 0) mbar_arrive(conv + s);
       }
     }
   } else {
@@ -432,7 +433,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int c = 0; c < 32; ++c) acc[c0 + c] += __uint_as_float(v[c]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(acc_free + buf);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free + buf);
       }
       if (row < M) {
         switch (ep.act) {

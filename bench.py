@@ -6,7 +6,7 @@ Metric (BASELINE.json): designed-CDR samples/sec, 100-step reverse diffusion, sy
 antibody-antigen complex (heavy 120 + light 110 + antigen 120), H3 design, random-init (seeded) weights,
 ESM disabled.  One "step" = one batched run of the whole sampler (`--samples-per-step` independent samples
 per GPU: t=1 prior draw, self-conditioning warm-up, 99 model+reverse steps, final x0 call = 101
-ScoreNetwork forwards = 2424 IPA layer-calls).  Under torchrun every rank runs its own samples of the same
+ScoreNetwork forwards = 2424 IPA layer-calls; default 8 samples per GPU per step).  Under torchrun every rank runs its own samples of the same
 complex (weak scaling, no data-path collective; inputs are broadcast from rank 0 once and the designed
 coordinates are gathered to rank 0 every step).
 
@@ -37,7 +37,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--samples-per-step', type=int, default=4, help='independent samples batched per GPU per step')
+    ap.add_argument('--samples-per-step', type=int, default=8, help='independent samples batched per GPU per step')
     ap.add_argument('--n-antigen', type=int, default=120, help='antigen residues (N = 230 + this)')
     ap.add_argument('--num-t', type=int, default=NUM_T)
     ap.add_argument('--cpu-steps', type=int, default=1, help='reverse iterations timed for the cpu_baseline sample')
