@@ -556,9 +556,10 @@ int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, i
   Epilogue ep{bias, residual, gate, row_scale, act, transpose_n, cm_n, cm_np};
   if (tile_n == 0) {
     // enough CTAs to cover the 148 SMs beats wide tiles for the small-M node GEMMs
-    const int mt = ceil_div(M, kBM);
-    if (Nout <= 32 || mt * ceil_div(Nout, 64) < 100) tile_n = 32;
-    else if (Nout <= 64 || mt * ceil_div(Nout, 128) < 100) tile_n = 64;
+    // the main loop costs about the same per k-slab for every tile width (barrier round trips, not bytes, pace
+    // it), so the widest tile that is not mostly padding wins even when it leaves SMs idle
+    if (Nout <= 32) tile_n = 32;
+    else if (Nout <= 64) tile_n = 64;
     else tile_n = 128;
   }
   switch (tile_n) {

@@ -670,16 +670,18 @@ __host__ inline size_t agg_smem_bytes(int N) {
 // ---------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-constexpr int kMaxSplits = 6;   // split-K factor of the final projection (2112 -> 256) when B*N is small
+constexpr int kMaxSplits = 8;   // split-K factor of the final projection (2112 -> 256) when B*N is small
 
 struct IpaWorkspace {
   float *proj, *Qdat, *Kdat, *Vdat, *probs, *feats, *bias, *partials;
   size_t total;
 };
 
+// The GEMM main loop costs about the same per 32-wide k-slab whatever the tile width, so the final projection
+// uses the widest tiles (128 columns: 2 per row block) and splits K so that every SM gets at most one tile.
 static int final_proj_splits(int M) {
-  const int tiles = ceil_div(M, 128) * (kC / 32);
-  int s = ceil_div(2 * 148, tiles);
+  const int tiles = ceil_div(M, 128) * (kC / 128);
+  int s = 148 / tiles;
   return s < 1 ? 1 : (s > kMaxSplits ? kMaxSplits : s);
 }
 
@@ -827,7 +829,7 @@ extern "C" int abx_ipa_forward(void* stream, int B, int N, const float* x, const
   int splits = final_proj_splits(M);
   const bool vec = ((uintptr_t)out % 16 == 0) && (!residual || (uintptr_t)residual % 16 == 0) && (!w->b_final || (uintptr_t)w->b_final % 16 == 0);
   if (splits > 1 && ws.partials && vec && gemm_backend() != 1 && gemm_tf32x3_supported(M, kC, kFeat, ws.feats, kFeat, w->w_final, kFeat)) {
-    if ((rc = launch_gemm_tf32x3_splitk(s, M, kC, kFeat, ws.feats, kFeat, w->w_final, kFeat, &splits, ws.partials, 32))) return rc;
+    if ((rc = launch_gemm_tf32x3_splitk(s, M, kC, kFeat, ws.feats, kFeat, w->w_final, kFeat, &splits, ws.partials, 128))) return rc;
     const int MN4 = M * kC / 4;
     ipa_finalize_kernel<<<ceil_div(MN4, 256), 256, 0, s>>>(MN4, splits, reinterpret_cast<const float4*>(ws.partials),
                                                           reinterpret_cast<const float4*>(w->b_final),
