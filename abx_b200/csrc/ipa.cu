@@ -347,8 +347,8 @@ __global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
 // (mma.sync m16n8k8 TF32, 3xTF32 operand split = fp32-level accuracy).
 //   logit = q_s.k_s + coef |Q-K|^2 + bias = [q_s, -2 coef Q] . [k_s, K] + coef |Q|^2 + coef |K|^2 + bias
 // i.e. one 28-long (padded to 32) inner product plus a row term and a key term, so the O(N^2) part is an MMA.
-// Pass 1 accumulates the row maximum and sum (online), pass 2 recomputes the scores, writes the normalised
-// probabilities (for the pair aggregation kernel) and multiplies them with the 40-wide value rows.  The key
+// One pass over the keys with an online softmax: the log-2 logits are stored for the pair aggregation kernel
+// (which normalises them with the final row max / sum), the probabilities multiply the 40-wide value rows.  The key
 // and value rows of the (b,h) slice are staged once per CTA in shared memory (row strides 36 / 44 floats:
 // conflict-free fragment loads).
 // ---------------------------------------------------------------------------------------------------
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kMW * 32) ipa_attention_mma_kernel(
     int N, const float* __restrict__ Qdat, const float* __restrict__ Kdat, const float* __restrict__ Vdat,
     const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
     const float* __restrict__ trans, const float* __restrict__ point_weights, float* __restrict__ probs,
-    float* __restrict__ feats) {
+    float* __restrict__ stats, float* __restrict__ feats) {
   extern __shared__ __align__(16) float sm[];
   const int Np = (N + 31) & ~31;
   float* Ks = sm;                            // [Np][36]: k_s (16), K points (12), zeros (8)
@@ -483,59 +483,53 @@ __global__ void __launch_bounds__(kMW * 32) ipa_attention_mma_kernel(
     }
   };
 
-  // ---- pass 1: row maximum and sum of exponentials
+  // ---- single pass over the keys: logits (log-2 units) go to the `probs` buffer, the softmax is online
+  //      (running max / sum per row, accumulator rescaled per 32-key chunk); the pair-aggregation kernel
+  //      normalises the stored logits with the final (max, 1/sum) written to `stats`.
   float m0 = -FLT_MAX, m1 = -FLT_MAX, l0 = 0.f, l1 = 0.f;
-  float bnext[4][4];
-  load_bias(0, bnext);
-  for (int j0 = 0; j0 < Np; j0 += 32) {
-    float s[4][4], bcur[4][4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) { bcur[n][0] = bnext[n][0]; bcur[n][1] = bnext[n][1]; bcur[n][2] = bnext[n][2]; bcur[n][3] = bnext[n][3]; }
-    load_bias(j0 + 32 < Np ? j0 + 32 : 0, bnext);          // next chunk (wraps to chunk 0 for pass 2)
-    scores(j0, bcur, s);
-    float c0 = -FLT_MAX, c1 = -FLT_MAX;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) { c0 = fmaxf(c0, fmaxf(s[n][0], s[n][1])); c1 = fmaxf(c1, fmaxf(s[n][2], s[n][3])); }
-    c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1)); c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
-    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1)); c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
-    const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);
-    l0 *= exp2f(m0 - n0); l1 *= exp2f(m1 - n1);
-    m0 = n0; m1 = n1;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) { l0 += exp2f(s[n][0] - m0) + exp2f(s[n][1] - m0); l1 += exp2f(s[n][2] - m1) + exp2f(s[n][3] - m1); }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-
-  // ---- pass 2: probabilities (written for the pair aggregation) and P V
   float oacc[5][4];
 #pragma unroll
   for (int m = 0; m < 5; ++m) oacc[m][0] = oacc[m][1] = oacc[m][2] = oacc[m][3] = 0.f;
   float* pr0 = probs + (bh * N + i0) * N;
   float* pr1 = probs + (bh * N + i1) * N;
   const bool w0 = r0 + g < N, w1 = r0 + g + 8 < N, vec2 = (N % 2) == 0;
+  float bnext[4][4];
+  load_bias(0, bnext);
   for (int j0 = 0; j0 < Np; j0 += 32) {
     float s[4][4], bcur[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) { bcur[n][0] = bnext[n][0]; bcur[n][1] = bnext[n][1]; bcur[n][2] = bnext[n][2]; bcur[n][3] = bnext[n][3]; }
     if (j0 + 32 < Np) load_bias(j0 + 32, bnext);
     scores(j0, bcur, s);
+    float c0 = -FLT_MAX, c1 = -FLT_MAX;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      c0 = fmaxf(c0, fmaxf(s[n][0], s[n][1])); c1 = fmaxf(c1, fmaxf(s[n][2], s[n][3]));
+      const int j = j0 + 8 * n + 2 * t;
+      if (vec2 && j + 1 < N) {
+        if (w0) *reinterpret_cast<float2*>(pr0 + j) = make_float2(s[n][0], s[n][1]);
+        if (w1) *reinterpret_cast<float2*>(pr1 + j) = make_float2(s[n][2], s[n][3]);
+      } else {
+        if (j < N) { if (w0) pr0[j] = s[n][0]; if (w1) pr1[j] = s[n][2]; }
+        if (j + 1 < N) { if (w0) pr0[j + 1] = s[n][1]; if (w1) pr1[j + 1] = s[n][3]; }
+      }
+    }
+    c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1)); c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1)); c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
+    const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);
+    const float k0 = exp2f(m0 - n0), k1 = exp2f(m1 - n1);
+    m0 = n0; m1 = n1;
+    l0 *= k0; l1 *= k1;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) { oacc[m][0] *= k0; oacc[m][1] *= k0; oacc[m][2] *= k1; oacc[m][3] *= k1; }
     float pacc[5][4];
 #pragma unroll
     for (int m = 0; m < 5; ++m) pacc[m][0] = pacc[m][1] = pacc[m][2] = pacc[m][3] = 0.f;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      const float p00 = exp2f(s[n][0] - m0) * inv0, p01 = exp2f(s[n][1] - m0) * inv0;
-      const float p10 = exp2f(s[n][2] - m1) * inv1, p11 = exp2f(s[n][3] - m1) * inv1;
-      const int j = j0 + 8 * n + 2 * t;
-      if (vec2 && j + 1 < N) {
-        if (w0) *reinterpret_cast<float2*>(pr0 + j) = make_float2(p00, p01);
-        if (w1) *reinterpret_cast<float2*>(pr1 + j) = make_float2(p10, p11);
-      } else {
-        if (j < N) { if (w0) pr0[j] = p00; if (w1) pr1[j] = p10; }
-        if (j + 1 < N) { if (w0) pr0[j + 1] = p01; if (w1) pr1[j + 1] = p11; }
-      }
+      const float p00 = exp2f(s[n][0] - m0), p01 = exp2f(s[n][1] - m0);
+      const float p10 = exp2f(s[n][2] - m1), p11 = exp2f(s[n][3] - m1);
+      l0 += p00 + p01; l1 += p10 + p11;
       uint32_t phi[4], plo[4];                       // A fragment: k-index t <-> key 2t, t+4 <-> key 2t+1
       split_tf32(p00, phi[0], plo[0]); split_tf32(p10, phi[1], plo[1]);
       split_tf32(p01, phi[2], plo[2]); split_tf32(p11, phi[3], plo[3]);
@@ -555,6 +549,15 @@ __global__ void __launch_bounds__(kMW * 32) ipa_attention_mma_kernel(
     }
 #pragma unroll
     for (int m = 0; m < 5; ++m) { oacc[m][0] += pacc[m][0]; oacc[m][1] += pacc[m][1]; oacc[m][2] += pacc[m][2]; oacc[m][3] += pacc[m][3]; }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+#pragma unroll
+  for (int m = 0; m < 5; ++m) { oacc[m][0] *= inv0; oacc[m][1] *= inv0; oacc[m][2] *= inv1; oacc[m][3] *= inv1; }
+  if (t == 0) {
+    if (w0) *reinterpret_cast<float2*>(stats + (bh * N + r0 + g) * 2) = make_float2(m0, inv0);
+    if (w1) *reinterpret_cast<float2*>(stats + (bh * N + r0 + g + 8) * 2) = make_float2(m1, inv1);
   }
 
   // ---- node features of these 16 rows (as in the SIMT kernel): via a per-warp tile [16][41]
@@ -602,13 +605,19 @@ constexpr int kAggThreads = 128, kAggWarps = kAggThreads / 32, kAggUnroll = 8;
 
 __global__ void __launch_bounds__(kAggThreads) ipa_pair_aggregate_kernel(int N, const float* __restrict__ z,
                                                                          const float* __restrict__ probs,
+                                                                         const float* __restrict__ stats,
                                                                          float* __restrict__ feats) {
   extern __shared__ __align__(16) float A[];        // [N][12] probabilities, then reused for the reduction
   const int i = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int h = wid; h < kH; h += kAggWarps) {
     const float* pr = probs + (((size_t)b * kH + h) * N + i) * N;
-    for (int j = lane; j < N; j += 32) A[j * kH + h] = __ldg(pr + j);
+    if (stats) {                                   // tensor-core attention path: log-2 logits + (row max, 1 / row sum)
+      const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + ((size_t)b * kH + h) * N + i);
+      for (int j = lane; j < N; j += 32) A[j * kH + h] = exp2f(__ldg(pr + j) - st.x) * st.y;
+    } else {
+      for (int j = lane; j < N; j += 32) A[j * kH + h] = __ldg(pr + j);
+    }
   }
   __syncthreads();
 
@@ -673,7 +682,7 @@ static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 constexpr int kMaxSplits = 8;   // split-K factor of the final projection (2112 -> 256) when B*N is small
 
 struct IpaWorkspace {
-  float *proj, *Qdat, *Kdat, *Vdat, *probs, *feats, *bias, *partials;
+  float *proj, *Qdat, *Kdat, *Vdat, *probs, *stats, *feats, *bias, *partials;
   size_t total;
 };
 
@@ -696,6 +705,7 @@ static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_fe
   w.Kdat = take(bn * kH * kQK);
   w.Vdat = take(bn * kH * kVD);
   w.probs = take(bn * kH * N);
+  w.stats = take(bn * kH * 2);
   w.feats = with_feats ? take(bn * kFeat) : nullptr;
   w.partials = (with_feats && final_proj_splits((int)bn) > 1) ? take((size_t)final_proj_splits((int)bn) * bn * kC) : nullptr;
   w.bias = with_bias ? take(bn * kH * N) : nullptr;
@@ -735,13 +745,15 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
     pair_bias = ws.bias;
   }
 
+  const float* agg_stats = nullptr;          // non-null: `probs` holds log-2 logits to be normalised with (max, 1/sum)
   const size_t msmem = attn_mma_smem_floats(N) * sizeof(float);
   if (attention_impl() == 0 && msmem <= 227 * 1024) {
     ABX_CUDA(cudaFuncSetAttribute(ipa_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
     ipa_attention_mma_kernel<<<dim3(ceil_div(N, 16 * kMW), kH, B), kMW * 32, msmem, s>>>(
-        N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, feats);
+        N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, ws.stats, feats);
     count_launch();
     if ((rc = check_launch("ipa_attention_mma_kernel"))) return rc;
+    agg_stats = ws.stats;
   } else {
     const size_t asmem = attn_smem_bytes(N);
     ABX_CUDA(cudaFuncSetAttribute(ipa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
@@ -753,7 +765,7 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
 
   const size_t gsmem = agg_smem_bytes(N);
   ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-  ipa_pair_aggregate_kernel<<<dim3(N, B), kAggThreads, gsmem, s>>>(N, z, ws.probs, feats);
+  ipa_pair_aggregate_kernel<<<dim3(N, B), kAggThreads, gsmem, s>>>(N, z, ws.probs, agg_stats, feats);
   count_launch();
   return check_launch("ipa_pair_aggregate_kernel");
 }
