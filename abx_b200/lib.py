@@ -46,6 +46,8 @@ SIGNATURES = {
     'abx_gemm_tf32x3_glu_cm': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
     'abx_gemm_tf32x3_batched_nt': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
     'abx_layernorm_cm': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, C.c_float, _vp]),
+    'abx_pair_input': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),
+    'abx_outer_product': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     'abx_layernorm': (_i, [_vp, C.c_longlong, _i, _vp, _vp, _vp, C.c_float, _i, _vp]),
     'abx_pair_attention': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     'abx_pair_attention_impl': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),

@@ -149,9 +149,8 @@ class OuterProductMean(nn.Module):
         m = mask.to(act.dtype)
         a = self.norm(act)
         left, right = self.left_proj(a, row_scale=m), self.right_proj(a, row_scale=m)
-        prod = left[:, None, :, :] * right[:, :, None, :]
-        diff = left[:, None, :, :] - right[:, :, None, :]
-        return self.out_proj(torch.cat([prod, diff], dim=-1), residual=residual)
+        from abx_b200 import ops
+        return self.out_proj(ops.outer_product(left, right), residual=residual)
 
 
 class TriangleMultiplication(nn.Module):
@@ -327,14 +326,22 @@ class EmbeddingAndSeqformer(nn.Module):
         te = get_timestep_embedding(batch['t'], c.index_embed_size)                                   # Embedder :93-119
         ab_seq = self.proj_aa_type(seq_t[:, :n_ab].long())
         seq_act = torch.cat([F.pad(ab_seq, (0, 0, 0, N - n_ab)) + seq_static, te[:, None, :].expand(B, N, -1)], dim=-1).float()
-        pair_act = torch.cat([pair_static.expand(B, -1, -1, -1), te[:, None, None, :].expand(B, N, N, -1),
-                              te[:, None, None, :].expand(B, N, N, -1)], dim=-1).float()
-        # _cross_concat: channel block 1 = t-embedding of residue i, block 2 = of residue j (both equal te[b])
-        if c.recycle_features:
-            if 'prev_seq' in batch:
-                seq_act = seq_act + self.prev_seq_norm(batch['prev_seq'])
-            if 'prev_pair' in batch:
+        # pair input in one kernel: concat(static, te_i, te_j) [_cross_concat: both blocks equal te[b]]
+        #   + LayerNorm(prev_pair) + proj_prev_pos[prev_pos]                                        (:193-222)
+        from abx_b200 import ops
+        use_prev = c.recycle_features and 'prev_pair' in batch
+        use_pos = c.recycle_pos and 'prev_pos' in batch
+        if pair_static.shape[0] == 1:
+            pair_act = ops.pair_input(pair_static, te, batch['prev_pair'] if use_prev else None,
+                                      self.prev_pair_norm if use_prev else None,
+                                      batch['prev_pos'] if use_pos else None, self.proj_prev_pos.weight if use_pos else None)
+        else:                    # per-element static embeddings (no complex-level cache): assemble with torch ops
+            pair_act = torch.cat([pair_static.expand(B, -1, -1, -1), te[:, None, None, :].expand(B, N, N, -1),
+                                  te[:, None, None, :].expand(B, N, N, -1)], dim=-1).float()
+            if use_prev:
                 pair_act = pair_act + self.prev_pair_norm(batch['prev_pair'])
-        if c.recycle_pos and 'prev_pos' in batch:
-            pair_act = pair_act + self.proj_prev_pos(batch['prev_pos'])
+            if use_pos:
+                pair_act = pair_act + self.proj_prev_pos(batch['prev_pos'])
+        if c.recycle_features and 'prev_seq' in batch:
+            seq_act = seq_act + self.prev_seq_norm(batch['prev_seq'])
         return self.seqformer(seq_act, pair_act, mask=batch['mask'], is_recycling=batch.get('is_recycling', True))

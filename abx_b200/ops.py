@@ -121,3 +121,35 @@ def triangle_product(x, w_glu, b_glu, pair_mask, norm_weight, norm_bias, eps=1e-
         lib.check(L_.abx_layernorm_cm(st, B, C, n, npad, lib.ptr(prod), lib.ptr(norm_weight.detach()), lib.ptr(norm_bias.detach()),
                                       float(eps), lib.ptr(out)))
     return out
+
+
+def pair_input(stat, te, prev_pair=None, norm=None, prev_pos=None, emb=None):
+    """concat(stat, te, te) + LayerNorm(prev_pair) + emb[prev_pos] in one kernel (seqformer.py:193-222).
+    stat [1|B?,N,N,Cs] (first element used), te [B,Ct], prev_pair [B,N,N,C], norm = nn.LayerNorm, prev_pos [B,N,N]."""
+    L_ = lib.load()
+    N, Cs = stat.shape[-2], stat.shape[-1]
+    B, Ct = te.shape
+    C = Cs + 2 * Ct
+    st = stat.reshape(-1, N, N, Cs)[0].float().contiguous()
+    tec = te.float().contiguous()
+    pp = prev_pair.float().contiguous() if prev_pair is not None else None
+    pos = prev_pos.long().contiguous() if prev_pos is not None else None
+    y = torch.empty(B, N, N, C, device=st.device, dtype=torch.float32)
+    with lib.device_guard(st):
+        lib.check(L_.abx_pair_input(lib.stream(), B, N, C, Cs, Ct, lib.ptr(st), lib.ptr(tec), lib.ptr(pp),
+                                    lib.ptr(norm.weight.detach()) if pp is not None else None,
+                                    lib.ptr(norm.bias.detach()) if pp is not None else None,
+                                    float(norm.eps) if pp is not None else 1e-5, lib.ptr(pos),
+                                    lib.ptr(emb.detach().float().contiguous()) if pos is not None else None, lib.ptr(y)))
+    return y
+
+
+def outer_product(left, right):
+    """[B,N,C] x2 -> [B,N,N,2C] = concat(left_j * right_i, left_j - right_i) (seqformer.py:392-407)."""
+    L_ = lib.load()
+    B, N, C = left.shape
+    l, r = left.float().contiguous(), right.float().contiguous()
+    out = torch.empty(B, N, N, 2 * C, device=l.device, dtype=torch.float32)
+    with lib.device_guard(l):
+        lib.check(L_.abx_outer_product(lib.stream(), B, N, C, lib.ptr(l), lib.ptr(r), lib.ptr(out)))
+    return out

@@ -155,6 +155,18 @@ int abx_layernorm_cm(void* stream, int B, int C, int n, int np, const float* x, 
 int abx_layernorm(void* stream, long long rows, int C, const float* x, const float* gamma, const float* beta,
                   float eps, int transpose_n, float* y);
 
+/* ---- pair-activation helpers of the trunk ----------------------------------------------------- */
+/* Pair input of EmbeddingAndSeqformer.forward (seqformer.py:193-222) in one pass:
+ *   y[b,i,j,:] = concat(stat[i,j,0:Cs], te[b,0:Ct], te[b,0:Ct]) + LayerNorm(prev_pair[b,i,j,:]) + emb[prev_pos[b,i,j],:]
+ * stat [N,N,Cs] (step-invariant pair embedding of the complex), te [B,Ct] timestep embedding, prev_pair [B,N,N,C]
+ * (NULL: term skipped) with LayerNorm gamma/beta [C], prev_pos [B,N,N] i64 + emb [bins,C] (NULL: skipped). */
+int abx_pair_input(void* stream, int B, int N, int C, int Cs, int Ct, const float* stat, const float* te,
+                   const float* prev_pair, const float* gamma, const float* beta, float eps,
+                   const int64_t* prev_pos, const float* emb, float* y);
+/* OuterProductMean features (seqformer.py:392-407): out[b,i,j,:] = concat(left[b,j,:] * right[b,i,:],
+ * left[b,j,:] - right[b,i,:]);  left, right [B,N,C], out [B,N,N,2C]. */
+int abx_outer_product(void* stream, int B, int N, int C, const float* left, const float* right, float* out);
+
 /* ---- attention with pair bias ------------------------------------------------------------------ */
 /* Attention core of seqformer.py:283-301 for TriangleAttention (:506-550), logits never materialised:
  *   out[b,s,i,h,:] = sum_j softmax_j(q[b,s,i,h,:].k[b,s,j,h,:]/sqrt(D) + bias[b,h,i,j]) v[b,s,j,h,:]

@@ -126,3 +126,29 @@ def test_triangle_product_matches_einsum(cuda_device, n):
     # second call reuses the cached channel-major buffers (pad columns must still be zero)
     out2 = ops.triangle_product(x, torch.cat(ws).contiguous(), torch.cat(bs).contiguous(), pm, g, be)
     assert torch.equal(out, out2)
+
+
+def test_pair_input_matches_torch(cuda_device):
+    from abx_b200 import ops
+    B, N, Cs, Ct = 3, 19, 128, 32
+    C = Cs + 2 * Ct
+    stat, te, prev = np_randn(70, 1, N, N, Cs).cuda(), np_randn(71, B, Ct).cuda(), (np_randn(72, B, N, N, C) * 2 + 1).cuda()
+    norm = torch.nn.LayerNorm(C).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(np_randn(73, C)); norm.bias.copy_(np_randn(74, C))
+    emb = np_randn(75, 15, C).cuda()
+    pos = torch.randint(0, 15, (B, N, N), generator=torch.Generator().manual_seed(0)).cuda()
+    base = torch.cat([stat.expand(B, -1, -1, -1), te[:, None, None, :].expand(B, N, N, -1), te[:, None, None, :].expand(B, N, N, -1)], -1)
+    with torch.no_grad():
+        ref = base + norm(prev) + emb[pos]
+        got = ops.pair_input(stat, te, prev, norm, pos, emb)
+        assert maxabs(got.cpu(), ref.cpu()) < 1e-5
+        assert torch.equal(ops.pair_input(stat, te), base)
+        assert maxabs(ops.pair_input(stat, te, prev, norm).cpu(), (base + norm(prev)).cpu()) < 1e-5
+
+
+def test_outer_product_matches_torch(cuda_device):
+    from abx_b200 import ops
+    left, right = np_randn(80, 2, 23, 32).cuda(), np_randn(81, 2, 23, 32).cuda()
+    ref = torch.cat([left[:, None, :, :] * right[:, :, None, :], left[:, None, :, :] - right[:, :, None, :]], dim=-1)
+    assert torch.equal(ops.outer_product(left, right), ref)
