@@ -19,7 +19,8 @@ def main():
             rows.append((r['Kernel Name'], float(r['Metric Value'].replace(',', ''))))
     agg = defaultdict(lambda: [0, 0.0])
     for name, ns in rows:
-        short = re.sub(r'\(.*', '', name)
+        short = re.sub(r'\(.*', '', name).replace('<unnamed>::', '').replace('(anonymous namespace)::', '')
+        short = re.sub(r'^void ', '', short)
         short = re.sub(r'<.*', '', short)[:90]
         agg[short][0] += 1
         agg[short][1] += ns
@@ -29,7 +30,7 @@ def main():
     print('|---|---:|---:|---:|---:|')
     for name, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
         print(f'| `{name}` | {n} | {ns / 1e6:.3f} | {100 * ns / total:.1f}% | {ns / n / 1e3:.1f} |')
-    ours = sum(v[1] for k, v in agg.items() if k.startswith('abx::'))
+    ours = sum(v[1] for k, v in agg.items() if 'abx::' in k)
     print(f'\nabx:: kernels: {100 * ours / total:.1f}% of kernel time')
 
 
