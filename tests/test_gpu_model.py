@@ -200,3 +200,38 @@ def test_inference_cli_end_to_end(cuda_device, tmp_path):
     from abx_b200.data.pdb_io import read_pdb_chains
     ref, des = read_pdb_chains(str(out / 'design' / 'reference' / 'tiny_H_L_A.pdb')), read_pdb_chains(str(out / 'design' / '0001' / 'tiny_H_L_A.pdb'))
     assert len(des['H']['str_seq']) == len(ref['H']['str_seq']) and des['L']['str_seq'] == ref['L']['str_seq']   # only H3 is designed
+
+
+def test_optimize_and_trajectory_modes(cuda_device, tmp_path):
+    """`--mode optimize` (noised start from forward_marginal at t = step/100, truncated reverse grid, OPT-<step> tree,
+    inference.py:201-205,339-345) and `--mode trajectory` (one PDB per step, :129,270-273) through the CLI."""
+    import json
+    import subprocess
+    import sys
+    import numpy as np
+    from abx_b200.data.synthetic import small_complex
+    from tests.test_io import _record
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    np.savez(tmp_path / 'tiny_H_L_A.npz', **_record(small_complex(batch_size=1)))
+    (tmp_path / 'names.idx').write_text('tiny_H_L_A\n')
+    cfg = json.load(open(os.path.join(root, 'abx_b200', 'config', 'config_model.json')))
+    cfg['model']['embeddings_and_seqformer']['esm']['enabled'] = False
+    cfg['diffuser']['so3'].update(num_sigma=100, num_omega=100, cache_dir=str(tmp_path / 'cache'))
+    (tmp_path / 'model.json').write_text(json.dumps(cfg))
+    feats = json.load(open(os.path.join(root, 'abx_b200', 'config', 'config_data_feature.json')))
+    for name, kw in feats:
+        if name == 'make_diffuser_features':
+            kw['optimize_steps'] = [4, 8]
+    (tmp_path / 'feats.json').write_text(json.dumps(feats))
+    base = [sys.executable, os.path.join(root, 'inference.py'), '--model', 'random:0', '--model_features', str(tmp_path / 'feats.json'),
+            '--model_config', str(tmp_path / 'model.json'), '--name_idx', str(tmp_path / 'names.idx'), '--data_dir', str(tmp_path)]
+    r = subprocess.run(base + ['--output_dir', str(tmp_path / 'o1'), '--mode', 'optimize', '--num_samples', '2'],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert sorted(os.listdir(tmp_path / 'o1' / 'optimize')) == ['OPT-4', 'OPT-8', 'reference']
+    assert sorted(os.listdir(tmp_path / 'o1' / 'optimize' / 'OPT-8')) == ['0000', '0001']
+    r = subprocess.run(base + ['--output_dir', str(tmp_path / 'o2'), '--mode', 'trajectory', '--num_samples', '1', '--num_t', '5'],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = sorted(os.listdir(tmp_path / 'o2' / 'trajectory' / '0000'))
+    assert len(files) == 5 and files[0].startswith('tiny_H_L_A@0.0100') and files[-1].startswith('tiny_H_L_A@1.0000')
