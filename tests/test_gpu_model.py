@@ -235,3 +235,39 @@ def test_optimize_and_trajectory_modes(cuda_device, tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     files = sorted(os.listdir(tmp_path / 'o2' / 'trajectory' / '0000'))
     assert len(files) == 5 and files[0].startswith('tiny_H_L_A@0.0100') and files[-1].startswith('tiny_H_L_A@1.0000')
+
+
+def test_full_size_sampler_properties(cuda_device):
+    """BASELINE-size complex (N = 350, H3 design), whole loop with CUDA-graph replay, size-independent properties:
+    finite designs, fixed residues keep their input frame and type, same seed -> same design, other seed -> other."""
+    from abx_b200 import sampler as S
+    from abx_b200.data.synthetic import synthetic_complex
+    from abx_b200.model import features as F_
+    from tests.gpu_util import built_diffuser
+    cfg = model_config()
+    fd = built_diffuser()
+    model = make_model(fd)
+    feats = json.load(open(os.path.join(ROOT, 'abx_b200', 'config', 'config_data_feature.json')))
+    for name, kw in feats:
+        if 'device' in kw:
+            kw['device'] = torch.device('cuda:0')
+        if name == 'make_diffuser_features':
+            kw.update(diff_conf=cfg['diffuser'], diffuser=fd)
+            kw.pop('optimize_steps', None)
+    raw = to_cuda(synthetic_complex(n_antigen=120, seed=1, batch_size=2))
+    outs = []
+    for seed in (3, 3, 4):
+        torch.manual_seed(seed)
+        gen = torch.Generator(device='cuda').manual_seed(seed)
+        batch = F_.FeatureBuilder(feats).build(dict(raw))
+        traj, final = S.sample_loop(batch, cfg, fd, model, num_t=4, generator=gen, cuda_graph=True)
+        outs.append((traj[-1]['atom14_results'].cpu(), traj[-1]['seq'].cpu(), final['rigids_t'].cpu().double(), batch))
+    a14, seq, rig, batch = outs[0]
+    n_ab = batch['anchor_flag'].shape[1]
+    assert a14.shape == (2, n_ab, 14, 3) and torch.isfinite(a14).all() and torch.isfinite(rig).all()
+    fixed = batch['fixed_mask'].bool().cpu()
+    assert int((~fixed).sum()) == 2 * 12                                   # H3 of the synthetic complex: 12 designed residues
+    assert maxabs(rig[fixed][:, 4:], batch['rigids_t'].cpu()[fixed][:, 4:].double()) < 1e-4
+    assert torch.equal(seq[fixed[:, :n_ab]], batch['seq_t'].cpu()[:, :n_ab][fixed[:, :n_ab]].clamp(0, 19))
+    assert torch.equal(outs[0][1], outs[1][1]) and maxabs(outs[0][0], outs[1][0]) < 1e-3   # same seed
+    assert maxabs(outs[0][2][~fixed], outs[2][2][~fixed]) > 1e-2                            # other seed, other frames
