@@ -33,6 +33,36 @@ int check_launch(const char* what);   // cudaGetLastError after a launch -> ABX_
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in
+// the stream is still draining; it must execute griddep_wait() before it touches anything the predecessor
+// wrote (the wait returns once the predecessor grid has completed and its writes are visible).  Both
+// instructions are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Scope flag set by a host-side pipeline (abx_ipa_forward) around a chain of short dependent kernels: launches
+// made through launch_kernel() inside the scope carry the PDL attribute.  Thread-local, so it never leaks into
+// another host thread's launches.
+bool pdl_scope_active();
+void pdl_scope_set(bool on);
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_scope_active() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- quaternion / rotation-vector algebra ----------------------------------------------------------
 // Real-first unit quaternions [w,x,y,z].  Templated on float/double: the model side of the reference
 // runs these in float32 (abx/model/quat_affine.py), the diffuser side in float64 once t is float64.

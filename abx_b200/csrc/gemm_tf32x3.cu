@@ -295,6 +295,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: the set-up above overlaps the tail of the previous kernel in the stream; nothing
+  // it wrote is touched before this point (no-ops for an ordinary launch)
+  griddep_wait();
+  griddep_launch_dependents();
 
   // Every role walks the same static schedule: this CTA's j-th tile is blockIdx.x + j gridDim.x (n fastest, so
   // CTAs running side by side share the A rows in L2); `it` = j nkb + kb counts k-slabs and drives the smem
@@ -536,9 +540,13 @@ int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, c
   }
   const int tiles = ceil_div(Nout, BN) * ceil_div(M, kBM) * splits * (bt.batches > 0 ? bt.batches : 1);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tf32x3_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(ma, mb, M, Nout, K, ep, y, ldy, trust_trunc(), kb_per_drain(),
-                                                                 splits, split_stride, bt);
+  const cudaError_t le = launch_kernel(gemm_tf32x3_kernel<BN>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, s, ma, mb, M, Nout, K, ep,
+                                       y, ldy, trust_trunc(), kb_per_drain(), splits, split_stride, bt);
   count_launch();
+  if (le != cudaSuccess) {
+    set_error("launch of gemm_tf32x3_kernel failed: %s", cudaGetErrorString(le));
+    return ABX_ERR_CUDA;
+  }
   return check_launch("gemm_tf32x3_kernel");
 }
 

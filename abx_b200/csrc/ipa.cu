@@ -38,6 +38,12 @@ constexpr int kOffKVP = kOffQP + 3 * kH * kPqk;     // 720: kv_point_local colum
 constexpr int kFeatPt = kH * kSv, kFeatNorm = kFeatPt + 3 * kH * kPv, kFeatPair = kFeatNorm + kH * kPv;
 static_assert(kProj == 1152 && kFeatPair + kH * kCz == kFeat, "IPA geometry");
 
+// bulk L2 prefetch of kPfChunk bytes (16-byte aligned address): no destination, the lines just land in L2
+constexpr unsigned kPfChunk = 4096;
+__device__ __forceinline__ void prefetch_l2_chunk(const char* p) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(kPfChunk) : "memory");
+}
+
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {   // streaming read: keep out of L1
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -56,6 +62,8 @@ __global__ void __launch_bounds__(256) ipa_pack_kernel(int B, int N, const float
                                                        const float* __restrict__ rots, const float* __restrict__ trans,
                                                        float* __restrict__ Qdat, float* __restrict__ Kdat,
                                                        float* __restrict__ Vdat) {
+  griddep_wait();                                    // proj comes from the node GEMM launched just before
+  griddep_launch_dependents();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * N * kH * kPackItems) return;
   const int item = idx % kPackItems, rest = idx / kPackItems;
@@ -364,8 +372,16 @@ __global__ void __launch_bounds__(kMW * 32) ipa_attention_mma_kernel(
     int N, const float* __restrict__ Qdat, const float* __restrict__ Kdat, const float* __restrict__ Vdat,
     const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
     const float* __restrict__ trans, const float* __restrict__ point_weights, float* __restrict__ probs,
-    float* __restrict__ stats, float* __restrict__ feats) {
+    float* __restrict__ stats, float* __restrict__ feats, const char* __restrict__ pf_base, unsigned pf_chunks) {
   extern __shared__ __align__(16) float sm[];
+  griddep_wait();                            // Qdat / Kdat / Vdat come from the pack kernel launched just before
+  griddep_launch_dependents();
+  // L2 warm-up for the pair aggregation kernel that follows: DRAM is mostly idle while this kernel runs on the
+  // tensor pipe, so lane 0 of every warp pulls one 4 KB chunk of [pf_base, pf_base + 4096 pf_chunks) — the head of
+  // z, which the aggregation kernel reads first — into L2 per key chunk (warp w takes chunks w, w + #warps, ...)
+  const unsigned pf_stride = gridDim.x * gridDim.y * gridDim.z * kMW;
+  unsigned pf_idx = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kMW + (threadIdx.x >> 5);
+  const bool pf_lane = (threadIdx.x & 31) == 0;
   const int Np = (N + 31) & ~31;
   float* Ks = sm;                            // [Np][36]: k_s (16), K points (12), zeros (8)
   float* Vs = Ks + (size_t)Np * kKS;         // [Np][44]: v_s (16), V points (24), pad
@@ -407,7 +423,11 @@ __global__ void __launch_bounds__(kMW * 32) ipa_attention_mma_kernel(
   __syncthreads();
 
   const int r0 = (blockIdx.x * kMW + warp) * 16;
-  if (r0 >= N) return;
+  if (r0 >= N) {                             // no query rows for this warp: issue its share of the prefetches and leave
+    if (pf_lane)
+      for (; pf_idx < pf_chunks; pf_idx += pf_stride) prefetch_l2_chunk(pf_base + (size_t)pf_idx * kPfChunk);
+    return;
+  }
   const int i0 = min(r0 + g, N - 1), i1 = min(r0 + g + 8, N - 1);
   // A fragments of [q_s, -2 coef Q, 0]: 4 k-steps of 8; row terms coef |Q_i|^2
   uint32_t qhi[4][4], qlo[4][4];
@@ -500,6 +520,7 @@ __global__ void __launch_bounds__(kMW * 32) ipa_attention_mma_kernel(
 #pragma unroll
     for (int n = 0; n < 4; ++n) { bcur[n][0] = bnext[n][0]; bcur[n][1] = bnext[n][1]; bcur[n][2] = bnext[n][2]; bcur[n][3] = bnext[n][3]; }
     if (j0 + 32 < Np) load_bias(j0 + 32, bnext);
+    if (pf_lane && pf_idx < pf_chunks) { prefetch_l2_chunk(pf_base + (size_t)pf_idx * kPfChunk); pf_idx += pf_stride; }
     scores(j0, bcur, s);
     float c0 = -FLT_MAX, c1 = -FLT_MAX;
 #pragma unroll
@@ -608,6 +629,8 @@ __global__ void __launch_bounds__(kAggThreads) ipa_pair_aggregate_kernel(int N, 
                                                                          const float* __restrict__ stats,
                                                                          float* __restrict__ feats) {
   extern __shared__ __align__(16) float A[];        // [N][12] probabilities, then reused for the reduction
+  griddep_wait();                                   // probs / stats come from the attention kernel launched just before
+  griddep_launch_dependents();
   const int i = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int h = wid; h < kH; h += kAggWarps) {
@@ -804,6 +827,7 @@ __host__ inline size_t agg_smem_bytes(int N) {
 // ---------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
+constexpr int kDefaultPrefetchMB = 64;   // measured on B200 (profiles/r01_ipa_pdl_ab.md): 0 -> 248 us, 32 -> 245, 64 -> 243, 96 -> 242 per B=8 layer-call
 constexpr int kMaxSplits = 8;   // split-K factor of the final projection (2112 -> 256) when B*N is small
 
 struct IpaWorkspace {
@@ -852,11 +876,44 @@ static int aggregate_impl() {
   return v;
 }
 
+// ABX_IPA_PDL=0 launches the kernels of a layer-call the ordinary way; default: programmatic dependent launch,
+// every kernel of the chain (node GEMM, pack, attention, pair aggregation, final projection, finalize) may start
+// while its predecessor drains and executes griddep_wait() before touching memory.
+static bool ipa_pdl() {
+  static bool v = [] { const char* e = getenv("ABX_IPA_PDL"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
+// ABX_IPA_PREFETCH_MB=<n>: the attention kernel warms L2 with the first n MB of z for the aggregation kernel
+// that follows it (0 = off).
+static size_t ipa_prefetch_bytes() {
+  static size_t v = [] { const char* e = getenv("ABX_IPA_PREFETCH_MB"); return (size_t)(e ? atoi(e) : kDefaultPrefetchMB) << 20; }();
+  return v;
+}
+
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(pdl_scope_active()) { pdl_scope_set(on); }
+  ~PdlScope() { pdl_scope_set(prev); }
+};
+
+#define ABX_LAUNCH(name, kernel, grid, block, smem, s, ...)                                  \
+  do {                                                                                       \
+    const cudaError_t le__ = launch_kernel(kernel, grid, block, smem, s, __VA_ARGS__);       \
+    count_launch();                                                                          \
+    if (le__ != cudaSuccess) {                                                               \
+      set_error("launch of " name " failed: %s", cudaGetErrorString(le__));                  \
+      return ABX_ERR_CUDA;                                                                   \
+    }                                                                                        \
+    if (int rc__ = check_launch(name)) return rc__;                                          \
+  } while (0)
+
 static int ipa_features(cudaStream_t s, int B, int N, const float* x, const float* z, const float* mask,
                         const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
                         float* feats, const IpaWorkspace& ws) {
   const int M = B * N;
   int rc;
+  PdlScope pdl(ipa_pdl());
   // node projections (folding.py:69-86): four Linear layers into one [M, 1152] buffer — one GEMM when the
   // caller provides the row-concatenated weights
   if (w->w_proj_cat) {
@@ -867,9 +924,8 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   if ((rc = launch_linear_f32(s, M, 3 * kH * kPqk, kC, x, kC, w->w_q_point, w->b_q_point, nullptr, 0, ws.proj + kOffQP, kProj))) return rc;
   if ((rc = launch_linear_f32(s, M, 3 * kH * (kPqk + kPv), kC, x, kC, w->w_kv_point, w->b_kv_point, nullptr, 0, ws.proj + kOffKVP, kProj))) return rc;
   }
-  ipa_pack_kernel<<<ceil_div(M * kH * kPackItems, 256), 256, 0, s>>>(B, N, ws.proj, rots, trans, ws.Qdat, ws.Kdat, ws.Vdat);
-  count_launch();
-  if ((rc = check_launch("ipa_pack_kernel"))) return rc;
+  ABX_LAUNCH("ipa_pack_kernel", ipa_pack_kernel, dim3(ceil_div(M * kH * kPackItems, 256)), dim3(256), 0, s, B, N, ws.proj, rots,
+             trans, ws.Qdat, ws.Kdat, ws.Vdat);
 
   if (pair_bias == nullptr) {
     ipa_pair_bias_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), 256, 0, s>>>(N, z, w->w_pair, w->b_pair, ws.bias);
@@ -882,10 +938,11 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   const size_t msmem = attn_mma_smem_floats(N) * sizeof(float);
   if (attention_impl() == 0 && msmem <= 227 * 1024) {
     ABX_CUDA(cudaFuncSetAttribute(ipa_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    ipa_attention_mma_kernel<<<dim3(ceil_div(N, 16 * kMW), kH, B), kMW * 32, msmem, s>>>(
-        N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, ws.stats, feats);
-    count_launch();
-    if ((rc = check_launch("ipa_attention_mma_kernel"))) return rc;
+    const size_t zbytes = (size_t)B * N * N * kCz * sizeof(float);
+    const size_t pfb = aggregate_impl() == 1 ? (ipa_prefetch_bytes() < zbytes ? ipa_prefetch_bytes() : zbytes) : 0;
+    ABX_LAUNCH("ipa_attention_mma_kernel", ipa_attention_mma_kernel, dim3(ceil_div(N, 16 * kMW), kH, B), dim3(kMW * 32), msmem, s, N,
+               ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, ws.stats, feats,
+               reinterpret_cast<const char*>(z), (unsigned)(pfb / kPfChunk));
     agg_stats = ws.stats;
   } else {
     const size_t asmem = attn_smem_bytes(N);
@@ -905,15 +962,17 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   }
   const size_t gsmem = agg_smem_bytes(N);
   ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-  ipa_pair_aggregate_kernel<<<dim3(N, B), kAggThreads, gsmem, s>>>(N, z, ws.probs, agg_stats, feats);
-  count_launch();
-  return check_launch("ipa_pair_aggregate_kernel");
+  ABX_LAUNCH("ipa_pair_aggregate_kernel", ipa_pair_aggregate_kernel, dim3(N, B), dim3(kAggThreads), gsmem, s, N, z, ws.probs,
+             agg_stats, feats);
+  return ABX_OK;
 }
 
 // out = sum_s partials[s] + bias (+ residual): the reduction of the split-K final projection
 __global__ void __launch_bounds__(256) ipa_finalize_kernel(int MN4, int splits, const float4* __restrict__ partials,
                                                            const float4* __restrict__ bias, const float4* __restrict__ residual,
                                                            float4* __restrict__ out) {
+  griddep_wait();                                   // partials come from the split-K GEMM launched just before
+  griddep_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= MN4) return;
   float4 a = partials[i];
@@ -974,6 +1033,7 @@ extern "C" int abx_ipa_forward(void* stream, int B, int N, const float* x, const
   IpaWorkspace ws = carve(workspace, B, N, pair_bias == nullptr, true);
   ABX_REQUIRE(workspace_bytes >= ws.total, "abx_ipa_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
   cudaStream_t s = (cudaStream_t)stream;
+  PdlScope pdl(ipa_pdl());
   if ((rc = ipa_features(s, B, N, x, z, mask, rots, trans, w, pair_bias, ws.feats, ws))) return rc;
   // final_proj (folding.py:130-132) + the residual of score_network.py:128.  With few rows the 2112-long
   // reduction is split across CTAs (split-K) and summed by a small kernel; otherwise one GEMM with fused epilogue.
@@ -983,11 +1043,10 @@ extern "C" int abx_ipa_forward(void* stream, int B, int N, const float* x, const
   if (splits > 1 && ws.partials && vec && gemm_backend() != 1 && gemm_tf32x3_supported(M, kC, kFeat, ws.feats, kFeat, w->w_final, kFeat)) {
     if ((rc = launch_gemm_tf32x3_splitk(s, M, kC, kFeat, ws.feats, kFeat, w->w_final, kFeat, &splits, ws.partials, 128))) return rc;
     const int MN4 = M * kC / 4;
-    ipa_finalize_kernel<<<ceil_div(MN4, 256), 256, 0, s>>>(MN4, splits, reinterpret_cast<const float4*>(ws.partials),
-                                                          reinterpret_cast<const float4*>(w->b_final),
-                                                          reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out));
-    count_launch();
-    return check_launch("ipa_finalize_kernel");
+    ABX_LAUNCH("ipa_finalize_kernel", ipa_finalize_kernel, dim3(ceil_div(MN4, 256)), dim3(256), 0, s, MN4, splits,
+               reinterpret_cast<const float4*>(ws.partials), reinterpret_cast<const float4*>(w->b_final),
+               reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out));
+    return ABX_OK;
   }
   return launch_linear_f32(s, M, kC, kFeat, ws.feats, kFeat, w->w_final, w->b_final, residual, 0, out, kC);
 }

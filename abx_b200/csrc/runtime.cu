@@ -17,6 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local bool g_pdl_scope = false;
+bool pdl_scope_active() { return g_pdl_scope; }
+void pdl_scope_set(bool on) { g_pdl_scope = on; }
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int check_launch(const char* what) {

@@ -20,6 +20,7 @@ def main():
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--precomputed-bias', type=int, default=1)
     ap.add_argument('--profile', type=int, default=0)
+    ap.add_argument('--graph', type=int, default=0, help='time G back-to-back layer-calls (same z, as IpaScore issues them) replayed from a CUDA graph')
     a = ap.parse_args()
     from abx_b200.model.folding import InvariantPointAttention
     from abx_b200.utils.weights import load_seeded_
@@ -47,6 +48,25 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
+    graph_ms = None
+    if a.graph:
+        side = torch.cuda.Stream()
+        with torch.no_grad(), torch.cuda.stream(side):
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg, stream=side):
+                keep = [ipa(x, z, mask, (rots, trans), pair_bias=bias) for _ in range(a.graph)]
+        torch.cuda.synchronize()
+        gt = []
+        for _ in range(a.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cg.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            gt.append(e0.elapsed_time(e1) / a.graph)
+        gt.sort()
+        graph_ms = gt[len(gt) // 2]
     if a.profile:
         from torch.profiler import ProfilerActivity, profile
         with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -66,7 +86,10 @@ def main():
         pass
     gbs = alg / (ms * 1e-3) / 1e9
     print(json.dumps(dict(B=B, N=N, ms_per_layer_call=ms, us_per_element=ms * 1e3 / B, algorithmic_bytes=alg,
-                          achieved_gbs=gbs, peak_gbs=peak, frac=gbs / peak, precomputed_bias=bool(a.precomputed_bias))))
+                          achieved_gbs=gbs, peak_gbs=peak, frac=gbs / peak, precomputed_bias=bool(a.precomputed_bias),
+                          graph_calls=a.graph, graph_ms_per_layer_call=graph_ms,
+                          graph_frac=(alg / (graph_ms * 1e-3) / 1e9 / peak) if graph_ms else None,
+                          pdl=os.environ.get('ABX_IPA_PDL', '1'), prefetch_mb=os.environ.get('ABX_IPA_PREFETCH_MB', '64'))))
 
 
 if __name__ == '__main__':
