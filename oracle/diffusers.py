@@ -298,3 +298,51 @@ class OracleDiffuser:
         seq_ref = m * seq_rand + (1 - m) * impute_seq
         trans_ref = trans_ref / torch.tensor(self.conf['r3']['coordinate_scaling'])
         return torch.cat([Q.rotvec_to_quat(rot_ref), trans_ref], dim=-1), seq_ref
+
+    def forward_marginal(self, rigids_0, seq_0, t, diffuse_mask, z_rot, u_rot, z_trans, x_t, dims, newval):
+        """full_diffuser.py:57-126 (optimize-mode start state) with the draws injected in reference order:
+        randn [B,N,3] / rand [B,N] (SO3Diffuser.sample, so3_diffuser.py:222-258), the unit normal behind
+        torch.normal(mean, std) (r3_diffuser.py:101), and the three categorical draws of
+        discrete_diffuser.py:72-127 (x_t [B,N], the perturbed position [B], its new value [B]).
+        Returns the reference's dict; `checks` holds the probability rows the categorical draws came from."""
+        assert self.cdf is not None and self.pdf is not None
+        B, N = seq_0.shape
+        cs = torch.tensor(self.conf['r3']['coordinate_scaling'])
+        rot_0 = Q.quat_to_rotvec(rigids_0[..., :4])                        # _extract_trans_rots :12-18
+        trans_0 = rigids_0[..., 4:]
+        # so3_diffuser.py:303-326
+        sampled = so3_sample(t, z_rot, u_rot, self.cdf, self.discrete_sigma, self.discrete_omega)
+        rot_score = so3_score_cached(sampled, t, self.score_norms, self.discrete_sigma, self.discrete_omega)
+        rot_t = Q.quat_to_rotvec(Q.quat_multiply(Q.rotvec_to_quat(rot_0), Q.rotvec_to_quat(sampled)))
+        # r3_diffuser.py:80-105
+        x0 = trans_0 * cs
+        lmc = (-0.5 * r3_marginal_b_t(t)).view(B, 1, 1)
+        mean, std = torch.exp(lmc) * x0, torch.sqrt(1.0 - torch.exp(2.0 * lmc))
+        xt = mean + std * z_trans
+        trans_score = r3_score(xt, x0, t, scale=False)
+        trans_t = xt / cs
+        # discrete_diffuser.py:72-127
+        S = self.rate.shape[0]
+        qt0 = seq_transition(t, self.eigvals, self.eigvecs)
+        rate = self.rate[None].expand(B, S, S)
+        x0c = torch.clamp(seq_0, min=0, max=S - 1).long()
+        bidx = torch.arange(B)[:, None].expand(B, N)
+        p_xt = qt0[bidx, x0c]                                               # rows the x_t draw came from [B,N,S]
+        rv = rate[bidx, x_t.long()].clone()
+        rv.scatter_(2, x_t.long()[..., None], 0.0)
+        p_dims = rv.sum(dim=2)                                              # [B,N] (unnormalised)
+        p_new = rv[torch.arange(B), dims.long()]                            # [B,S]
+        seq_t = x_t.clone()
+        seq_t[torch.arange(B), dims.long()] = newval.to(seq_t.dtype)
+        rot_scaling, trans_scaling = self.score_scaling(t)
+        if diffuse_mask is not None:
+            m = diffuse_mask
+            rot_t = m[..., None] * rot_t + (1 - m[..., None]) * rot_0
+            trans_t = m[..., None] * trans_t + (1 - m[..., None]) * trans_0
+            trans_score = m[..., None] * trans_score
+            rot_score = m[..., None] * rot_score
+            seq_t = m * seq_t + (1 - m) * seq_0
+        return {'rigids_t': torch.cat([Q.rotvec_to_quat(rot_t), trans_t], dim=-1), 'trans_score': trans_score,
+                'rot_score': rot_score, 'trans_score_scaling': trans_scaling, 'rot_score_scaling': rot_scaling,
+                'seq_t': seq_t, 'q_t0': qt0, 'rate_t': rate,
+                'checks': {'p_xt': p_xt, 'p_dims': p_dims, 'p_new': p_new}}

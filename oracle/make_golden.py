@@ -5,7 +5,7 @@ Build-container only; committed together with its outputs.  The reference has no
 vectors of its own, so these files are what pins the oracle — and, through the
 oracle, the CUDA path — to the reference.
 
-    python oracle/make_golden.py [geometry igso3 scores reverse prior ipa ipascore model sampler]
+    python oracle/make_golden.py [geometry igso3 scores reverse prior marginal ipa ipascore model sampler]
 """
 import contextlib
 import json
@@ -208,6 +208,59 @@ def gen_prior():
          seq_rand=log[3][1], rigids_t=ret['rigids_t'], seq_t=ret['seq_t'])
 
 
+def gen_marginal():
+    """FullDiffuser.forward_marginal (full_diffuser.py:57-126): the optimize-mode start state.  Draw order of the
+    reference: randn [B,N,3] + rand [B,N] (SO3Diffuser.sample), normal [B,N,3] (R3Diffuser.forward_marginal:101),
+    three multinomial draws (DiscreteDiffuser.forward_marginal: x_t, the perturbed position, its new value)."""
+    fd = get_diffuser()
+    g = torch.Generator().manual_seed(21)
+    B, N = 3, 37
+    q = torch.randn(B, N, 4, generator=g); q = q / q.norm(dim=-1, keepdim=True)
+    x = torch.randn(B, N, 3, generator=g) * 12
+    rig = torch.cat([q, x], dim=-1)
+    seq = torch.randint(0, 20, (B, N), generator=g)
+    mask = (torch.rand(B, N, generator=g) < 0.5).to(torch.int32)
+    t = torch.tensor([0.02, 0.2, 0.7])            # sigma rows 19, 199, 699: all held by tests/golden/igso3.npz
+
+    log = []
+    orig = {n: getattr(torch, n) for n in ('randn', 'rand', 'normal', 'multinomial')}
+
+    def wrap(n):
+        def f(*a, **k):
+            if n == 'normal':                              # recover the unit draw behind mean + std * z
+                state = torch.get_rng_state()
+                out = orig[n](*a, **k)
+                after = torch.get_rng_state()
+                torch.set_rng_state(state)
+                z = orig['randn'](out.shape)
+                torch.set_rng_state(after)
+                assert torch.allclose(k['mean'] + k['std'] * z, out, atol=1e-6), 'normal() is not mean + std * randn here'
+                log.append((n, z))
+                return out
+            out = orig[n](*a, **k)
+            log.append((n, out.clone()))
+            return out
+        return f
+    for n in orig:
+        setattr(torch, n, wrap(n))
+    try:
+        torch.manual_seed(11)
+        ret = fd.forward_marginal(rigids_0=rig, seq_0=seq, t=t, diffuse_mask=mask)
+        torch.manual_seed(12)
+        ret_nomask = fd.forward_marginal(rigids_0=rig, seq_0=seq, t=t, diffuse_mask=None)
+    finally:
+        for n, f in orig.items():
+            setattr(torch, n, f)
+    kinds = [k for k, _ in log]
+    assert kinds == ['randn', 'rand', 'normal', 'multinomial', 'multinomial', 'multinomial'] * 2, kinds
+    out = dict(rigids_0=rig, seq_0=seq, mask=mask, t=t)
+    for tag, r, lg in (('m', ret, log[:6]), ('n', ret_nomask, log[6:])):
+        out.update({f'{tag}_z_rot': lg[0][1], f'{tag}_u_rot': lg[1][1], f'{tag}_z_trans': lg[2][1],
+                    f'{tag}_x_t': lg[3][1].reshape(B, N), f'{tag}_dims': lg[4][1].reshape(B), f'{tag}_newval': lg[5][1].reshape(B)})
+        out.update({f'{tag}_{k}': v for k, v in r.items()})
+    save('marginal', **out)
+
+
 # ------------------------------------------------------------------------------------------------
 def _ref_features(n_antigen=9, batch_size=2, generate_area='H3', seed=0):
     from abx.model.features import FeatureBuilder
@@ -352,7 +405,7 @@ def gen_sampler():
     save('sampler', **arrays, diffuse_mask=diffuse_mask, **out)
 
 
-ALL = dict(geometry=gen_geometry, igso3=gen_igso3, scores=gen_scores, reverse=gen_reverse, prior=gen_prior,
+ALL = dict(geometry=gen_geometry, igso3=gen_igso3, scores=gen_scores, reverse=gen_reverse, prior=gen_prior, marginal=gen_marginal,
            ipa=gen_ipa, ipascore=gen_ipascore, model=gen_model, sampler=gen_sampler)
 
 if __name__ == '__main__':

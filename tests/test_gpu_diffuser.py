@@ -206,6 +206,57 @@ def test_prior_sample_matches_oracle(cuda_device):
     assert maxabs(out['rigids_t'].cpu(), r_o) < 1e-4
 
 
+def test_forward_marginal_matches_oracle(cuda_device):
+    """forward_marginal (full_diffuser.py:57-126, optimize-mode start state) on the device; the draws the product
+    makes (randn, rand, normal, 3 x multinomial — the reference's order) are captured and replayed through the oracle."""
+    from tests.gpu_util import reference_table_diffuser
+    g = golden('marginal')
+    fd = reference_table_diffuser()
+    od = oracle_diffuser()
+    rig, seq, t = g['rigids_0'].cuda(), g['seq_0'].cuda(), g['t'].cuda()
+    B, N = seq.shape
+    for mask in (g['mask'], None):
+        log = []
+        orig = {n: getattr(torch, n) for n in ('randn', 'rand', 'normal', 'multinomial')}
+
+        def wrap(n):
+            def f(*a, **k):
+                out = orig[n](*a, **k)
+                if n == 'normal':
+                    log.append((n, ((out.double() - k['mean'].double()) / k['std'].double()).float().cpu()))
+                else:
+                    log.append((n, out.clone().cpu()))
+                return out
+            return f
+        for n in orig:
+            setattr(torch, n, wrap(n))
+        try:
+            torch.manual_seed(3)
+            out = fd.forward_marginal(rig, seq, t, diffuse_mask=None if mask is None else mask.cuda())
+        finally:
+            for n, f in orig.items():
+                setattr(torch, n, f)
+        assert [k for k, _ in log] == ['randn', 'rand', 'normal', 'multinomial', 'multinomial', 'multinomial']
+        ref = od.forward_marginal(g['rigids_0'], g['seq_0'], g['t'], mask, log[0][1], log[1][1], log[2][1],
+                                  log[3][1].reshape(B, N), log[4][1].reshape(B), log[5][1].reshape(B))
+        assert torch.equal(out['seq_t'].cpu().long(), ref['seq_t'].long())
+        assert maxabs(out['rigids_t'].cpu(), ref['rigids_t']) < 1e-4
+        assert maxabs(out['rot_score'].cpu(), ref['rot_score']) < 1e-4 * max(1.0, float(ref['rot_score'].abs().max()))
+        assert maxabs(out['trans_score'].cpu(), ref['trans_score']) < 1e-4
+        assert maxabs(out['q_t0'].cpu(), ref['q_t0']) < 1e-6 and maxabs(out['rate_t'].cpu(), ref['rate_t']) < 1e-7
+        assert maxabs(out['trans_score_scaling'].cpu(), ref['trans_score_scaling']) < 1e-5
+        assert maxabs(out['rot_score_scaling'].cpu(), ref['rot_score_scaling']) < 1e-3
+        # draws are admissible: every categorical draw has positive probability under the oracle's rows
+        c = ref['checks']
+        assert float(torch.gather(c['p_xt'], 2, log[3][1].reshape(B, N, 1).long()).min()) > 0
+        assert float(torch.gather(c['p_dims'], 1, log[4][1].reshape(B, 1).long()).min()) > 0
+        assert float(torch.gather(c['p_new'], 1, log[5][1].reshape(B, 1).long()).min()) > 0
+        if mask is not None:                                       # fixed residues keep x0 exactly (translation, type)
+            fixed = mask == 0
+            assert maxabs(out['rigids_t'][..., 4:].cpu()[fixed], g['rigids_0'][..., 4:][fixed]) == 0
+            assert torch.equal(out['seq_t'].cpu().long()[fixed], g['seq_0'].long()[fixed])
+
+
 def test_no_cpu_fallback(cuda_device):
     from abx_b200.lib import AbxError
     from tests.gpu_util import built_diffuser

@@ -97,3 +97,24 @@ def test_prior_sample_matches_reference():
                              g['seq_rand'])
     assert torch.equal(seq.long(), g['seq_t'].long())
     assert maxabs(rig, g['rigids_t']) < 1e-5
+
+
+def test_forward_marginal_matches_reference():
+    """Optimize-mode start state (full_diffuser.py:57-126), masked and unmasked, draws replayed."""
+    g = golden('marginal')
+    od = oracle_diffuser()
+    for tag, mask in (('m', g['mask']), ('n', None)):
+        out = od.forward_marginal(g['rigids_0'], g['seq_0'], g['t'], mask, g[f'{tag}_z_rot'], g[f'{tag}_u_rot'],
+                                  g[f'{tag}_z_trans'], g[f'{tag}_x_t'], g[f'{tag}_dims'], g[f'{tag}_newval'])
+        assert torch.equal(out['seq_t'].long(), g[f'{tag}_seq_t'].long())
+        assert maxabs(out['rigids_t'], g[f'{tag}_rigids_t']) < 1e-5
+        assert maxabs(out['rot_score'], g[f'{tag}_rot_score']) < 1e-4 * max(1.0, float(g[f'{tag}_rot_score'].abs().max()))
+        assert maxabs(out['trans_score'], g[f'{tag}_trans_score']) < 1e-4
+        assert maxabs(out['q_t0'], g[f'{tag}_q_t0']) < 1e-6 and maxabs(out['rate_t'], g[f'{tag}_rate_t']) == 0
+        assert maxabs(out['rot_score_scaling'], g[f'{tag}_rot_score_scaling']) < 1e-5
+        assert maxabs(out['trans_score_scaling'], g[f'{tag}_trans_score_scaling']) < 1e-5
+        # the categorical draws are possible under the rows the oracle derives (positive probability)
+        c = out['checks']
+        assert float(torch.gather(c['p_xt'], 2, g[f'{tag}_x_t'].long()[..., None]).min()) > 0
+        assert float(torch.gather(c['p_dims'], 1, g[f'{tag}_dims'].long()[:, None]).min()) > 0
+        assert float(torch.gather(c['p_new'], 1, g[f'{tag}_newval'].long()[:, None]).min()) > 0
