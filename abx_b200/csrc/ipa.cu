@@ -15,6 +15,8 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace abx {
@@ -368,7 +370,7 @@ __host__ __device__ inline size_t attn_mma_smem_floats(int N) {
   return (size_t)Np * (kKS + kVS) + 2 * (size_t)Np + (size_t)kMW * 16 * (kVD + 1);
 }
 
-__global__ void __launch_bounds__(kMW * 32) ipa_attention_mma_kernel(
+__global__ void __launch_bounds__(kMW * 32, 2) ipa_attention_mma_kernel(
     int N, const float* __restrict__ Qdat, const float* __restrict__ Kdat, const float* __restrict__ Vdat,
     const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
     const float* __restrict__ trans, const float* __restrict__ point_weights, float* __restrict__ probs,
@@ -827,6 +829,7 @@ __host__ inline size_t agg_smem_bytes(int N) {
 // ---------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
+constexpr int kDefaultOverlapChunks = 0, kMaxOverlapChunks = 4;
 constexpr int kDefaultPrefetchMB = 64;   // measured on B200 (profiles/r01_ipa_pdl_ab.md): 0 -> 248 us, 32 -> 245, 64 -> 243, 96 -> 242 per B=8 layer-call
 constexpr int kMaxSplits = 8;   // split-K factor of the final projection (2112 -> 256) when B*N is small
 
@@ -908,6 +911,44 @@ struct PdlScope {
     if (int rc__ = check_launch(name)) return rc__;                                          \
   } while (0)
 
+// ABX_IPA_OVERLAP=<c> (2..4): software pipeline inside a layer-call.  The batch is cut into c chunks; the attention
+// kernel of chunk k+1 (tensor-pipe / latency bound, DRAM nearly idle) runs on a high-priority side stream while the
+// pair aggregation of chunk k (HBM bound) runs on the caller's stream.  Fork / join are events, so the pattern is
+// legal under stream capture.  0 / unset = one attention and one aggregation launch for the whole batch.
+static int ipa_overlap_chunks() {
+  const char* e = getenv("ABX_IPA_OVERLAP");
+  const int v = e ? atoi(e) : kDefaultOverlapChunks;
+  return v < 2 ? 1 : (v > kMaxOverlapChunks ? kMaxOverlapChunks : v);
+}
+
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, done[kMaxOverlapChunks] = {};
+  bool ready = false;
+};
+
+// Per-device side stream + events, created on the first call that is not being captured (resource creation is not
+// allowed while a capture in global mode is under way); nullptr = not available for this call.
+static SideStream* side_stream(cudaStream_t main_stream) {
+  static SideStream pool[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& ss = pool[dev];
+  if (ss.ready) return &ss;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(main_stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&ss.stream, cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
+  bool ok = cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < kMaxOverlapChunks && ok; ++k) ok = cudaEventCreateWithFlags(&ss.done[k], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); return nullptr; }
+  ss.ready = true;
+  return &ss;
+}
+
 static int ipa_features(cudaStream_t s, int B, int N, const float* x, const float* z, const float* mask,
                         const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
                         float* feats, const IpaWorkspace& ws) {
@@ -938,6 +979,34 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   const size_t msmem = attn_mma_smem_floats(N) * sizeof(float);
   if (attention_impl() == 0 && msmem <= 227 * 1024) {
     ABX_CUDA(cudaFuncSetAttribute(ipa_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    const int chunks = aggregate_impl() == 1 ? (ipa_overlap_chunks() < B ? ipa_overlap_chunks() : B) : 1;
+    SideStream* ss = chunks > 1 ? side_stream(s) : nullptr;
+    if (ss) {
+      // attention of chunk k+1 on the side stream || aggregation of chunk k on the caller's stream
+      PdlScope plain(false);                       // event edges only between the two streams
+      const size_t gsmem = agg_smem_bytes(N);
+      ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+      ABX_CUDA(cudaEventRecord(ss->fork, s));
+      ABX_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+      const size_t n1 = (size_t)N, hnn = (size_t)kH * N * N;
+      int b0 = 0;
+      for (int k = 0; k < chunks; ++k) {
+        const int nb = (B - b0) / (chunks - k);    // even split, larger chunks last
+        const size_t zoff = (size_t)b0 * n1 * n1 * kCz, zbytes = (size_t)nb * n1 * n1 * kCz * sizeof(float);
+        const size_t pfb = k == 0 ? (ipa_prefetch_bytes() < zbytes ? ipa_prefetch_bytes() : zbytes) : 0;
+        ABX_LAUNCH("ipa_attention_mma_kernel", ipa_attention_mma_kernel, dim3(ceil_div(N, 16 * kMW), kH, nb), dim3(kMW * 32), msmem,
+                   ss->stream, N, ws.Qdat + (size_t)b0 * kH * n1 * kQK, ws.Kdat + (size_t)b0 * kH * n1 * kQK,
+                   ws.Vdat + (size_t)b0 * kH * n1 * kVD, pair_bias + b0 * hnn, mask + (size_t)b0 * n1, rots + (size_t)b0 * n1 * 9,
+                   trans + (size_t)b0 * n1 * 3, w->point_weights, ws.probs + b0 * hnn, ws.stats + (size_t)b0 * kH * n1 * 2,
+                   feats + (size_t)b0 * n1 * kFeat, reinterpret_cast<const char*>(z + zoff), (unsigned)(pfb / kPfChunk));
+        ABX_CUDA(cudaEventRecord(ss->done[k], ss->stream));
+        ABX_CUDA(cudaStreamWaitEvent(s, ss->done[k], 0));
+        ABX_LAUNCH("ipa_pair_aggregate_kernel", ipa_pair_aggregate_kernel, dim3(N, nb), dim3(kAggThreads), gsmem, s, N, z + zoff,
+                   ws.probs + b0 * hnn, ws.stats + (size_t)b0 * kH * n1 * 2, feats + (size_t)b0 * n1 * kFeat);
+        b0 += nb;
+      }
+      return ABX_OK;
+    }
     const size_t zbytes = (size_t)B * N * N * kCz * sizeof(float);
     const size_t pfb = aggregate_impl() == 1 ? (ipa_prefetch_bytes() < zbytes ? ipa_prefetch_bytes() : zbytes) : 0;
     ABX_LAUNCH("ipa_attention_mma_kernel", ipa_attention_mma_kernel, dim3(ceil_div(N, 16 * kMW), kH, B), dim3(kMW * 32), msmem, s, N,
@@ -962,8 +1031,7 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   }
   const size_t gsmem = agg_smem_bytes(N);
   ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-  ABX_LAUNCH("ipa_pair_aggregate_kernel", ipa_pair_aggregate_kernel, dim3(N, B), dim3(kAggThreads), gsmem, s, N, z, ws.probs,
-             agg_stats, feats);
+  ABX_LAUNCH("ipa_pair_aggregate_kernel", ipa_pair_aggregate_kernel, dim3(N, B), dim3(kAggThreads), gsmem, s, N, z, ws.probs, agg_stats, feats);
   return ABX_OK;
 }
 

@@ -89,7 +89,7 @@ def main():
                           achieved_gbs=gbs, peak_gbs=peak, frac=gbs / peak, precomputed_bias=bool(a.precomputed_bias),
                           graph_calls=a.graph, graph_ms_per_layer_call=graph_ms,
                           graph_frac=(alg / (graph_ms * 1e-3) / 1e9 / peak) if graph_ms else None,
-                          pdl=os.environ.get('ABX_IPA_PDL', '1'), prefetch_mb=os.environ.get('ABX_IPA_PREFETCH_MB', '64'))))
+                          pdl=os.environ.get('ABX_IPA_PDL', '1'), overlap=os.environ.get('ABX_IPA_OVERLAP', '0'), prefetch_mb=os.environ.get('ABX_IPA_PREFETCH_MB', '64'))))
 
 
 if __name__ == '__main__':
