@@ -225,7 +225,9 @@ int abx_ipa_pair_bias(void* stream, int B, int N, const float* z, const float* w
  *   x [B,N,C]; z [B,N,N,Cz]; mask [B,N] f32; rots [B,N,3,3]; trans [B,N,3] (already / position_scale)
  *   pair_bias: [B,H,N,N] from abx_ipa_pair_bias, or NULL (then computed into the workspace)
  *   residual: optional [B,N,C] added to the output (score_network.py:128: seq_act += attn)
- *   out [B,N,C] */
+ *   out [B,N,C]
+ * Limits: 1 <= N <= 1536 (ABX_ERR_INVALID beyond; the tensor-core attention kernel serves N <= 640, the SIMT one the
+ * rest); x and z 16-byte aligned.  The kernels of one call are chained with programmatic dependent launch on `stream`. */
 int abx_ipa_forward(void* stream, int B, int N, const float* x, const float* z, const float* mask,
                     const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
                     const float* residual, float* out, void* workspace, size_t workspace_bytes);

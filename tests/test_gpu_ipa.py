@@ -46,9 +46,10 @@ def test_ipa_matches_reference_golden(cuda_device):
     assert maxabs(out.cpu(), g['out']) < 2e-5 * float(g['out'].abs().max())
 
 
-@pytest.mark.parametrize('B,N', [(1, 1), (1, 33), (3, 100), (2, 350)])
+@pytest.mark.parametrize('B,N', [(1, 1), (1, 33), (3, 100), (2, 350), (1, 700), (1, 1536)])
 def test_ipa_matches_oracle(cuda_device, B, N):
-    """Ragged masks, sizes off the tile grid, and the north-star size; features and output."""
+    """Ragged masks, sizes off the tile grid, the north-star size, a size beyond the tensor-core attention kernel's
+    shared-memory capacity (N > 640: the SIMT attention kernel takes over) and the supported maximum; features and output."""
     ipa, P = make_ipa()
     gen = torch.Generator().manual_seed(100 + N)
     x, z = np_randn(300 + N, B, N, 256), np_randn(400 + N, B, N, N, 128)
