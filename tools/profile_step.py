@@ -19,6 +19,7 @@ def main():
     ap.add_argument('--n-antigen', type=int, default=120)
     ap.add_argument('--num-t', type=int, default=3)
     ap.add_argument('--linear-breakdown', type=int, default=1)
+    ap.add_argument('--glue', type=int, default=0, help='attribute the torch (non-abx) device time to python source lines')
     a = ap.parse_args()
     import __graft_entry__
     __graft_entry__.build()
@@ -71,6 +72,25 @@ def main():
         print(f'linear calls: {len(recs)}, total {tot:.1f} ms (includes input .contiguous() copies)')
         for key, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
             print(f'  {ms:8.2f} ms  {n:4d} x {ms / n:7.3f}  (M,N,K,act,res,gate,contig)={key}')
+    if a.glue:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+            run()
+            torch.cuda.synchronize()
+        rows = {}
+        for e in prof.key_averages(group_by_stack_n=12):
+            if e.self_device_time_total <= 0 or 'abx::' in e.key or 'Memcpy' in e.key:
+                continue
+            frames = [f for f in e.stack if '/abx_b200/' in f or '/bench.py' in f]
+            where = frames[0].split('/abx_b200/')[-1] if frames else (e.stack[0] if e.stack else '?')
+            r = rows.setdefault((e.key, where), [0, 0.0])
+            r[0] += e.count
+            r[1] += e.self_device_time_total
+        tot = sum(v[1] for v in rows.values())
+        print(f'torch-op device time: {tot / 1e3:.2f} ms over {a.num_t + 1} forwards (B={a.B})')
+        for (op, where), (n, us) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:40]:
+            print(f'  {us / 1e3:8.3f} ms {n:5d} x {us / n:8.1f} us  {op[:36]:36s} {where[:110]}')
+        return
     t0 = time.perf_counter()
     run()
     torch.cuda.synchronize()
