@@ -5,10 +5,11 @@ Build-container only; committed together with its outputs.  The reference has no
 vectors of its own, so these files are what pins the oracle — and, through the
 oracle, the CUDA path — to the reference.
 
-    python oracle/make_golden.py [geometry igso3 scores reverse prior marginal ipa ipascore model sampler]
+    python oracle/make_golden.py [geometry igso3 scores reverse reverse_edges prior marginal ipa ipascore model sampler]
 """
 import contextlib
 import json
+import math
 import os
 import sys
 import time
@@ -188,6 +189,60 @@ def gen_reverse():
             torch.distributions.poisson.Poisson.__init__ = orig
         out[f'{tag}_rate_dt'] = captured['rate']
     save('reverse', **out)
+
+
+def gen_reverse_edges():
+    """FullDiffuser.reverse on the corner cases of the quaternion <-> rotation-vector maps and of the tau-leap:
+    identity / w < 0 / w = 0 (angle pi) / 1e-8 rad input rotations, zero rotation perturbation (zero score and zero
+    noise: the |theta| < 1e-6 series of rotvec_to_quat, quat_affine.py:133-150), saturated logits, residue indices 0 /
+    19 / 20, and multiple jumps per residue that leave [0, 19] before the clamp (discrete_diffuser.py:181-187)."""
+    fd = get_diffuser()
+    g = torch.Generator().manual_seed(31)
+    B, N = 2, 16
+    q = torch.randn(B, N, 4, generator=g, dtype=torch.float64); q = q / q.norm(dim=-1, keepdim=True)
+    eps = 1e-8
+    special = torch.tensor([[1.0, 0, 0, 0], [1.0, 0, 0, 0], [-0.6, 0.8, 0, 0], [-0.6, 0, 0.8, 0], [0, 1.0, 0, 0], [0, 0, 0.6, 0.8],
+                            [math.cos(eps / 2), math.sin(eps / 2), 0, 0], [math.cos(eps / 2), 0, 0, -math.sin(eps / 2)]],
+                           dtype=torch.float64)
+    q[:, :8] = special
+    x = torch.randn(B, N, 3, generator=g, dtype=torch.float64) * 12
+    rigid_t = torch.cat([q, x], dim=-1)
+    mask = torch.zeros(B, N, dtype=torch.int32)
+    mask[:, 1::2] = 1                                   # odd residues diffused, even ones fixed
+    mask[1, 8:] = 1
+    seq_t = torch.randint(0, 20, (B, N), generator=g)
+    seq_t[0, 0], seq_t[0, 1], seq_t[0, 2], seq_t[0, 3] = 20, 20, 0, 19
+    rot_score = torch.randn(B, N, 3, generator=g) * 0.7
+    rot_score[:, 8:12] = 0                              # with zero noise below: perturbation exactly zero
+    trans_score = (torch.randn(B, N, 3, generator=g) * 0.5).double()
+    logits = torch.randn(B, N, 20, generator=g) * 2
+    logits[0, 4] = -60.0; logits[0, 4, 7] = 60.0        # saturated softmax
+    logits[0, 5] = 0.0                                  # uniform
+    t = torch.tile(torch.tensor(np.float64(0.5)), (B,))
+    dt = torch.tensor(1 / 100)
+    jumps = torch.zeros(B, N, 20)
+    jumps[0, 3, 0] = 2; jumps[0, 3, 5] = 1              # 19 + 2 (0 - 19) + (5 - 19) < 0 -> clamp to 0
+    jumps[0, 2, 19] = 3                                 # 0 + 3 * 19 > 19 -> clamp to 19
+    jumps[1, 9, 4] = 1; jumps[1, 11, 11] = 1; jumps[0, 1, 6] = 1
+    orig_randn, orig_poisson = torch.randn, torch.poisson
+    drawn = []
+
+    def randn(*a, **k):
+        z = orig_randn(*a, **k)
+        if len(drawn) == 0:
+            z[:, 8:12] = 0                              # rotation noise of residues 8..11
+        drawn.append(z.clone())
+        return z
+    torch.randn, torch.poisson = randn, (lambda rate, *a, **k: jumps.to(rate.dtype))
+    try:
+        torch.manual_seed(77)
+        rigids_1, seq_1 = fd.reverse(rigid_t=rigid_t, seq_t=seq_t, rot_score=rot_score, trans_score=trans_score,
+                                     logits_t=logits, t=t, dt=dt, diffuse_mask=mask, center=True, noise_scale=1.0)
+    finally:
+        torch.randn, torch.poisson = orig_randn, orig_poisson
+    assert len(drawn) == 2 and torch.isfinite(rigids_1).all()
+    save('reverse_edges', rigid_t=rigid_t, seq_t=seq_t, rot_score=rot_score, trans_score=trans_score, logits=logits, mask=mask,
+         t=t, z_rot=drawn[0], z_trans=drawn[1], jumps=jumps, rigids_1=rigids_1, seq_1=seq_1)
 
 
 def gen_prior():
@@ -405,7 +460,7 @@ def gen_sampler():
     save('sampler', **arrays, diffuse_mask=diffuse_mask, **out)
 
 
-ALL = dict(geometry=gen_geometry, igso3=gen_igso3, scores=gen_scores, reverse=gen_reverse, prior=gen_prior, marginal=gen_marginal,
+ALL = dict(geometry=gen_geometry, igso3=gen_igso3, scores=gen_scores, reverse=gen_reverse, reverse_edges=gen_reverse_edges, prior=gen_prior, marginal=gen_marginal,
            ipa=gen_ipa, ipascore=gen_ipascore, model=gen_model, sampler=gen_sampler)
 
 if __name__ == '__main__':

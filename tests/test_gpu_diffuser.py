@@ -146,6 +146,21 @@ def test_reverse_step_matches_reference(cuda_device):
         assert torch.equal(seq_c.cpu(), seq_o.long()) and maxabs(rig_c.cpu(), rig_o) < tol
 
 
+def test_reverse_step_corner_cases(cuda_device):
+    """The reverse-step kernel on the corner cases of tests/golden/reverse_edges.npz (identity / w < 0 / angle-pi /
+    1e-8 rad rotations, zero perturbation, saturated logits, clamped indices, multi-jump tau-leaps): residue types
+    bit-exact, frames within 1e-9 of the reference's float64 result."""
+    from tests.gpu_util import reference_table_diffuser
+    p = golden('reverse_edges')
+    fd = reference_table_diffuser()
+    c = {k: v.cuda() for k, v in p.items()}
+    rig, seq = fd.reverse(c['rigid_t'], c['seq_t'], c['rot_score'], c['trans_score'], c['logits'], c['t'], torch.tensor(1 / 100),
+                          diffuse_mask=c['mask'], noise=(c['z_rot'], c['z_trans'], c['jumps']))
+    assert rig.dtype == torch.float64 and bool(torch.isfinite(rig).all())
+    assert torch.equal(seq.cpu(), p['seq_1'].long())
+    assert maxabs(rig.cpu(), p['rigids_1']) < 1e-9
+
+
 def test_reverse_draws_noise_in_reference_order(cuda_device):
     """Default path draws randn, randn, poisson (same shapes/order as the reference) from the CUDA generator."""
     from tests.gpu_util import reference_table_diffuser

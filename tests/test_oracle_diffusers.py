@@ -90,6 +90,19 @@ def test_reverse_step_matches_reference():
         assert maxabs(rig, p['rigids_1']) < 1e-9
 
 
+def test_reverse_step_corner_cases_match_reference():
+    """Identity / w < 0 / angle-pi / 1e-8 rad rotations, zero perturbation, saturated logits, clamped residue indices
+    and multi-jump tau-leaps (tests/golden/reverse_edges.npz, written by the reference's FullDiffuser.reverse)."""
+    p = golden('reverse_edges')
+    od = oracle_diffuser()
+    rig, seq = od.reverse(p['rigid_t'], p['seq_t'], p['rot_score'], p['trans_score'], p['logits'], p['t'], torch.tensor(1 / 100),
+                          p['mask'], p['z_rot'], p['z_trans'], p['jumps'])
+    assert torch.isfinite(rig).all() and rig.dtype == torch.float64
+    assert torch.equal(seq.long(), p['seq_1'].long())
+    assert maxabs(rig, p['rigids_1']) < 1e-9
+    assert int(seq[0, 3]) == 0 and int(seq[0, 2]) == 0 and int(seq[0, 1]) == 6     # clamp (diffused), fixed keeps 0, one jump
+
+
 def test_prior_sample_matches_reference():
     g = golden('prior')
     od = oracle_diffuser()
