@@ -2,6 +2,9 @@
 // eps inside the square root; reference: every `LayerNorm(...)` of abx/model/seqformer.py and
 // score_network.py:117-135).  One warp per row, the row held in registers (two-pass mean / variance),
 // 16-byte loads and stores: the kernel is a pure HBM stream (read C floats, write C floats per row).
+// The number of float4 per lane is a template parameter (KV = ceil(C / 128)): with the generic 8-deep predicated
+// loops the C = 192 pair LayerNorm issued ~340 warp instructions per row and was issue-bound at 3.7 TB/s
+// (ncu: issue slots 72 % busy, DRAM 44 %; profiles/r01_trunk_kernels_ncu.md).
 //
 // Optional output transposition of the two middle dimensions of a [B, n, n, C] tensor (row (b,i,j) is
 // written to (b,j,i)), which replaces the `rearrange(pair_act, 'b i j c -> b j i c')` copy in front of the
@@ -12,6 +15,7 @@ namespace abx {
 
 constexpr int kLnWarps = 8, kLnMaxV = 8;   // up to 8 float4 per lane: C <= 1024
 
+template <int KV>
 __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
     long long rows, int C, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
     float eps, int transpose_n, float* __restrict__ y) {
@@ -20,10 +24,10 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
   if (row >= rows) return;
   const int nv = C >> 2;                        // float4 per row
   const float4* xr = reinterpret_cast<const float4*>(x + row * C);
-  float4 v[kLnMaxV];
+  float4 v[KV];
   float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxV; ++k) {
+  for (int k = 0; k < KV; ++k) {
     const int i = lane + 32 * k;
     if (i < nv) {
       v[k] = xr[i];
@@ -33,7 +37,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
   const float mean = warp_sum(sum) / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxV; ++k) {
+  for (int k = 0; k < KV; ++k) {
     const int i = lane + 32 * k;
     if (i < nv) {
       const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
@@ -43,15 +47,21 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
   const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
   long long orow = row;
   if (transpose_n > 0) {
-    const long long nn = (long long)transpose_n * transpose_n;
-    const long long b = row / nn, r = row % nn;
-    orow = b * nn + (r % transpose_n) * transpose_n + r / transpose_n;
+    if (rows <= 0xffffffffLL) {                  // 32-bit index arithmetic: 64-bit divisions cost ~100 instructions each
+      const unsigned n = (unsigned)transpose_n, nn = n * n, r32 = (unsigned)row;
+      const unsigned b = r32 / nn, r = r32 - b * nn, i = r / n, j = r - i * n;
+      orow = (long long)b * nn + (long long)j * n + i;
+    } else {
+      const long long nn = (long long)transpose_n * transpose_n;
+      const long long b = row / nn, r = row % nn;
+      orow = b * nn + (r % transpose_n) * transpose_n + r / transpose_n;
+    }
   }
   float4* yr = reinterpret_cast<float4*>(y + orow * C);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int k = 0; k < kLnMaxV; ++k) {
+  for (int k = 0; k < KV; ++k) {
     const int i = lane + 32 * k;
     if (i < nv) {
       const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
@@ -124,7 +134,17 @@ extern "C" int abx_layernorm(void* stream, long long rows, int C, const float* x
   ABX_REQUIRE(transpose_n == 0 || x != y, "abx_layernorm: the transposing form cannot run in place");
   const long long blocks = (rows + kLnWarps - 1) / kLnWarps;
   ABX_REQUIRE(blocks < 2147483647LL, "abx_layernorm: too many rows");
-  layernorm_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, (cudaStream_t)stream>>>(rows, C, x, gamma, beta, eps, transpose_n, y);
+  const int kv = ((C >> 2) + 31) / 32;          // float4 per lane
+  auto launch = [&](auto kern) { kern<<<(unsigned)blocks, kLnWarps * 32, 0, (cudaStream_t)stream>>>(rows, C, x, gamma, beta, eps, transpose_n, y); };
+  switch (kv) {
+    case 1: launch(layernorm_kernel<1>); break;
+    case 2: launch(layernorm_kernel<2>); break;
+    case 3: launch(layernorm_kernel<3>); break;
+    case 4: launch(layernorm_kernel<4>); break;
+    case 5: launch(layernorm_kernel<5>); break;
+    case 6: launch(layernorm_kernel<6>); break;
+    default: launch(layernorm_kernel<kLnMaxV>); break;
+  }
   count_launch();
   return check_launch("layernorm_kernel");
 }
