@@ -1,21 +1,20 @@
-// Invariant Point Attention (abx/model/folding.py:47-132) as a pipeline of sm_100a kernels:
+// Invariant Point Attention (abx/model/folding.py:47-132) on sm_100a — host pipeline of one layer-call:
 //
-//   node GEMMs (linear.cu)     x -> [q_scalar | kv_scalar | q_point_local | kv_point_local]      :69-86
-//   ipa_pack_kernel            rigid transform of the points into the global frame, per-head packing :89-93
-//   ipa_pair_bias_kernel       sqrt(1/3) (z W_pair^T + b), head-major [B,H,N,N]  (once per IpaScore) :101-104
-//   ipa_attention_kernel       logits (scalar + point distance + pair bias), mask, softmax,
-//                              attention over scalar / point values, inverse rigid transform, norms :79-123
-//   ipa_pair_aggregate_kernel  o_pair[i,h,:] = sum_j a[h,i,j] z[i,j,:]  — the O(N^2 Cz) HBM stream   :126-127
-//   node GEMM                  final_proj over the 2112-wide feature row                           :130-132
+//   node GEMM (gemm_tf32x3.cu)   x -> [q_scalar | kv_scalar | q_point_local | kv_point_local]        :69-86
+//   ipa_pack_nodes_kernel        rigid transform of the points into the global frame, per-residue packing :89-93
+//   ipa_fused_kernel             logits (scalar + point distance + pair bias), mask, online softmax, attention
+//   (ipa_fused.cu)               over scalar / point values and over the pair activations — z read ONCE — inverse
+//                                rigid transform, norms: the 2112-wide feature row                   :79-128
+//   node GEMM (split-K)          final_proj over the feature row (+ bias + residual)                 :130-132
 //
-// Data layout (all fp32): z [B,N,N,128] row-major as the reference holds it; per-head node operands
-// Qdat/Kdat [B,H,N,28] (16 scalar channels + 4 points x 3) and Vdat [B,H,N,40] (16 + 8 points x 3);
-// probabilities and pair bias head-major [B,H,N,N] so that both the attention kernel (fixed h, rows of
-// j) and the aggregation kernel (fixed i, 12 rows of j) read contiguous runs.
+//   ipa_pair_bias_kernel         sqrt(1/3) (z W_pair^T + b), head-major [B,H,N,N]: depends on z and the weights
+//                                only, so IpaScore evaluates it once for its 8 weight-shared iterations :101-104
+//
+// The round-1 two-kernel core (tensor-core attention writing log-2 logits + pair-aggregation stream) is kept
+// behind ABX_IPA_FUSED=0 for A/B measurements.
+// Data layout (all fp32): z [B,N,N,128] row-major as the reference holds it; pair bias head-major [B,H,N,N].
 #include <float.h>
 #include <stdlib.h>
-
-#include <mutex>
 
 #include "common.cuh"
 
@@ -148,209 +147,11 @@ __global__ void __launch_bounds__(256) ipa_pair_bias_kernel(int N, const float* 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// attention: one CTA per (b, h, 32 query rows).  The 32 x N logit tile lives in shared memory (row
-// stride odd -> conflict-free with lanes on rows), so the softmax is the exact two-pass one.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kRows = 32, kAttnThreads = 256, kAttnWarps = kAttnThreads / 32, kOld = kVD + 1;
-constexpr int kKeyChunk = 8;                        // keys per cp.async stage of a warp
-constexpr int kStageFloats = kKeyChunk * kVD;       // one stage holds 8 key rows (28 floats) or 8 value rows (40)
-
-__host__ __device__ inline int attn_ld(int N) { return N | 1; }
-__host__ __device__ inline size_t attn_tile_floats(int N) {
-  size_t a = (size_t)kRows * attn_ld(N), b = (size_t)kAttnWarps * kRows * kOld;
-  return ((a > b ? a : b) + 3) & ~(size_t)3;        // keep the staging area 16-byte aligned
-}
-__host__ inline size_t attn_smem_bytes(int N) {
-  return (attn_tile_floats(N) + (size_t)kAttnWarps * 2 * kStageFloats) * sizeof(float);
-}
-
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Stage `nkeys` consecutive rows of `row_floats` floats (a multiple of 4) from global into a warp-private buffer.
-__device__ __forceinline__ void stage_rows(float* dst, const float* src, int nkeys, int row_floats, int lane) {
-  const int n4 = nkeys * row_floats / 4;
-  for (int i = lane; i < n4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
-}
-
-__global__ void __launch_bounds__(kAttnThreads) ipa_attention_kernel(
-    int N, const float* __restrict__ Qdat, const float* __restrict__ Kdat, const float* __restrict__ Vdat,
-    const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
-    const float* __restrict__ trans, const float* __restrict__ point_weights, float* __restrict__ probs,
-    float* __restrict__ feats) {
-  extern __shared__ __align__(16) float S[];
-  __shared__ float O[kRows][kOld];
-  const int ld = attn_ld(N);
-  const int i0 = blockIdx.x * kRows, h = blockIdx.y, b = blockIdx.z;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const size_t bh = (size_t)b * kH + h;
-
-  // 1. pair-bias tile -> S (coalesced along j)
-  const float* bias_bh = bias + bh * N * N;
-  for (int r = wid; r < kRows; r += kAttnWarps) {
-    int i = i0 + r;
-    if (i < N)
-      for (int j = lane; j < N; j += 32) S[r * ld + j] = __ldg(bias_bh + (size_t)i * N + j);
-  }
-  __syncthreads();
-
-  // 2. logits: lane = query row; each warp owns a contiguous range of keys and streams their packed rows
-  //    through a warp-private double buffer with cp.async, so the key operands are shared-memory broadcasts
-  const int per_warp = (N + kAttnWarps - 1) / kAttnWarps;
-  const int jb = min(N, wid * per_warp), je = min(N, jb + per_warp);
-  float* stage = S + attn_tile_floats(N) + (size_t)wid * 2 * kStageFloats;
-  {
-    const int i = i0 + lane;
-    const bool row_ok = i < N;
-    float q[kQK];
-    if (row_ok) {
-      const float4* qp = reinterpret_cast<const float4*>(Qdat + (bh * N + i) * kQK);
-#pragma unroll
-      for (int k = 0; k < kQK / 4; ++k) { float4 v = __ldg(qp + k); q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w; }
-    } else {
-#pragma unroll
-      for (int k = 0; k < kQK; ++k) q[k] = 0.f;
-    }
-    const float pw = __ldg(point_weights + h);
-    const float gamma = (pw > 20.f) ? pw : log1pf(expf(pw));                    // F.softplus  folding.py:96
-    const float coef = -0.5f * sqrtf(1.0f / (3.0f * kPqk * 9.0f / 2.0f)) * gamma;   // -1/2 w_point gamma  :97-99
-    const float mi = row_ok ? __ldg(mask + (size_t)b * N + i) : 0.f;
-    const float* Kbh = Kdat + bh * N * kQK;
-    if (jb < je) stage_rows(stage, Kbh + (size_t)jb * kQK, min(kKeyChunk, je - jb), kQK, lane);
-    cp_async_commit();
-    int buf = 0;
-    for (int jc = jb; jc < je; jc += kKeyChunk, buf ^= 1) {
-      const int nk = min(kKeyChunk, je - jc);
-      if (jc + kKeyChunk < je)
-        stage_rows(stage + (buf ^ 1) * kStageFloats, Kbh + (size_t)(jc + kKeyChunk) * kQK, min(kKeyChunk, je - jc - kKeyChunk), kQK, lane);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncwarp();
-      const float* kbuf = stage + buf * kStageFloats;
-#pragma unroll 2
-      for (int t = 0; t < nk; ++t) {
-        const int j = jc + t;
-        const float4* kp = reinterpret_cast<const float4*>(kbuf + t * kQK);
-        float k[kQK];
-#pragma unroll
-        for (int u = 0; u < kQK / 4; ++u) { float4 v = kp[u]; k[4 * u] = v.x; k[4 * u + 1] = v.y; k[4 * u + 2] = v.z; k[4 * u + 3] = v.w; }
-        float2 dot2 = make_float2(0.f, 0.f), dd2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < kSqk; c += 2) dot2 = __ffma2_rn(make_float2(q[c], q[c + 1]), make_float2(k[c], k[c + 1]), dot2);
-#pragma unroll
-        for (int c = kSqk; c < kQK; c += 2) {
-          const float2 d = make_float2(q[c] - k[c], q[c + 1] - k[c + 1]);
-          dd2 = __ffma2_rn(d, d, dd2);
-        }
-        const float dot = dot2.x + dot2.y, d2 = dd2.x + dd2.y;
-        if (row_ok) {
-          float lg = (dot + coef * d2) + S[lane * ld + j];
-          bool ok = (mi * __ldg(mask + (size_t)b * N + j)) != 0.f;                // mask_2d  folding.py:106-109
-          S[lane * ld + j] = ok ? lg : -FLT_MAX;
-        }
-      }
-      __syncwarp();                                  // the buffer being refilled next round is no longer read
-    }
-    cp_async_wait<0>();
-  }
-  __syncthreads();
-
-  // 3. softmax over j, one warp per row; probabilities go to global (for the pair aggregation) and stay in S
-  for (int r = wid; r < kRows; r += kAttnWarps) {
-    int i = i0 + r;
-    if (i >= N) continue;
-    float* Sr = S + r * ld;
-    float mx = -FLT_MAX;
-    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, Sr[j]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < N; j += 32) { float e = expf(Sr[j] - mx); Sr[j] = e; sum += e; }
-    sum = warp_sum(sum);
-    float* pr = probs + (bh * N + i) * N;
-    for (int j = lane; j < N; j += 32) { float p = Sr[j] / sum; Sr[j] = p; pr[j] = p; }
-  }
-  __syncthreads();
-
-  // 4. scalar + point values: lane = row, each warp accumulates over its key range (value rows streamed like
-  //    the key rows), then an 8-way reduction through smem
-  {
-    float2 acc[kVD / 2];
-#pragma unroll
-    for (int d = 0; d < kVD / 2; ++d) acc[d] = make_float2(0.f, 0.f);
-    const float* Vbh = Vdat + bh * N * kVD;
-    if (jb < je) stage_rows(stage, Vbh + (size_t)jb * kVD, min(kKeyChunk, je - jb), kVD, lane);
-    cp_async_commit();
-    int buf = 0;
-    for (int jc = jb; jc < je; jc += kKeyChunk, buf ^= 1) {
-      const int nk = min(kKeyChunk, je - jc);
-      if (jc + kKeyChunk < je)
-        stage_rows(stage + (buf ^ 1) * kStageFloats, Vbh + (size_t)(jc + kKeyChunk) * kVD, min(kKeyChunk, je - jc - kKeyChunk), kVD, lane);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncwarp();
-      const float* vbuf = stage + buf * kStageFloats;
-#pragma unroll 2
-      for (int t = 0; t < nk; ++t) {
-        const float sv = S[lane * ld + jc + t];
-        const float4* vp = reinterpret_cast<const float4*>(vbuf + t * kVD);
-#pragma unroll
-        for (int u = 0; u < kVD / 4; ++u) {
-          const float4 v = vp[u];
-          acc[2 * u] = __ffma2_rn(make_float2(sv, sv), make_float2(v.x, v.y), acc[2 * u]);
-          acc[2 * u + 1] = __ffma2_rn(make_float2(sv, sv), make_float2(v.z, v.w), acc[2 * u + 1]);
-        }
-      }
-      __syncwarp();
-    }
-    cp_async_wait<0>();
-    __syncthreads();                       // everyone is done reading S; reuse it for the partial sums
-    float* P = S + (size_t)(wid * kRows + lane) * kOld;
-#pragma unroll
-    for (int d = 0; d < kVD / 2; ++d) { P[2 * d] = acc[d].x; P[2 * d + 1] = acc[d].y; }
-  }
-  __syncthreads();
-  for (int o = threadIdx.x; o < kRows * kVD; o += kAttnThreads) {
-    int r = o / kVD, d = o % kVD;
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < kAttnWarps; ++w) v += S[(size_t)(w * kRows + r) * kOld + d];
-    O[r][d] = v;
-  }
-  __syncthreads();
-
-  // 5. write the node features of these rows
-  for (int o = threadIdx.x; o < kRows * kSv; o += kAttnThreads) {
-    int r = o / kSv, c = o % kSv, i = i0 + r;
-    if (i < N) feats[((size_t)b * N + i) * kFeat + h * kSv + c] = O[r][c];      // 'b i h c -> b i (h c)'
-  }
-  {
-    int r = threadIdx.x / kPv, p = threadIdx.x % kPv, i = i0 + r;               // 32 rows x 8 points = 256 threads
-    if (i < N) {
-      const size_t bn = (size_t)b * N + i;
-      float R[9], t[3];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = __ldg(rots + bn * 9 + k);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) t[k] = __ldg(trans + bn * 3 + k);
-      // invert_rigids (r3.py:54-59): R^T, -(R^T t); then rigids_apply  folding.py:121
-      float it[3], g[3], l[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) it[k] = -(R[k] * t[0] + R[3 + k] * t[1] + R[6 + k] * t[2]);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) g[k] = O[r][kSv + 3 * p + k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) l[k] = it[k] + (R[k] * g[0] + R[3 + k] * g[1] + R[6 + k] * g[2]);
-      float* f = feats + bn * kFeat;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) f[kFeatPt + k * (kH * kPv) + h * kPv + p] = l[k];      // '(r n)'  folding.py:122
-      f[kFeatNorm + h * kPv + p] = sqrtf(l[0] * l[0] + l[1] * l[1] + l[2] * l[2] + 1e-8f);   // :123
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // attention on the tensor cores (default): one warp per 16 query rows, FlashAttention-2 style fragments
@@ -694,131 +495,6 @@ __global__ void __launch_bounds__(kAggThreads) ipa_pair_aggregate_kernel(int N, 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// pair aggregation, TMA version (opt-in, ABX_IPA_AGGREGATE=tma): same result as ipa_pair_aggregate_kernel, but the z[i, :, :] row block
-// (N x 512 B, contiguous) is streamed by the bulk-copy engine: one producer lane issues cp.async.bulk copies of
-// 16-row chunks (8 KB) into a 4-deep shared-memory ring guarded by mbarriers, four consumer warps multiply the
-// rows with the 12 per-head probabilities (24 FFMA2 per 16 bytes) and hand the slots back.  The copies in flight
-// (32 KB per CTA, four CTAs per SM) no longer depend on registers or on the consumers' issue slots.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kTmaRows = 16, kTmaStages = 4, kTmaThreads = 160;    // 4 consumer warps + 1 producer warp
-constexpr int kTmaChunkFloats = kTmaRows * kCz;
-
-__host__ __device__ inline size_t agg_tma_smem_bytes(int N) {
-  const size_t a = (((size_t)N * kH + 31) & ~(size_t)31) * sizeof(float);            // probabilities [N][12]
-  return a + (size_t)kTmaStages * kTmaChunkFloats * sizeof(float) + 2 * kTmaStages * sizeof(uint64_t) + 128;
-}
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-
-__global__ void __launch_bounds__(kTmaThreads) ipa_pair_aggregate_tma_kernel(int N, const float* __restrict__ z,
-                                                                             const float* __restrict__ probs,
-                                                                             const float* __restrict__ stats,
-                                                                             float* __restrict__ feats) {
-  extern __shared__ __align__(128) float smf[];
-  const size_t a_floats = ((size_t)N * kH + 31) & ~(size_t)31;
-  float* A = smf;                                                   // [N][12]
-  float* ring = smf + a_floats;                                     // [stages][16 rows][128]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kTmaStages * kTmaChunkFloats);
-  uint64_t* empty = full + kTmaStages;
-  const int i = blockIdx.x, b = blockIdx.y;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int nchunks = (N + kTmaRows - 1) / kTmaRows;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kTmaStages; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(full + s)), "r"(1) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(empty + s)), "r"(4) : "memory");
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (wid == 4) {
-    // ---- producer: bulk copies of consecutive z rows of block (b, i)
-    if (lane == 0) {
-      const float* zrow = z + ((size_t)b * N + i) * N * kCz;
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % kTmaStages;
-        const uint32_t ph = (c / kTmaStages) & 1;
-        mbar_wait_parity(empty + s, ph ^ 1);
-        const int rows = min(kTmaRows, N - c * kTmaRows);
-        const uint32_t bytes = (uint32_t)rows * kCz * sizeof(float);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(full + s)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_addr(ring + (size_t)s * kTmaChunkFloats)), "l"(zrow + (size_t)c * kTmaChunkFloats), "r"(bytes),
-                       "r"(smem_addr(full + s)) : "memory");
-      }
-    }
-    return;
-  }
-
-  // ---- consumers: stage the probabilities of row i (12 heads x N keys), then eat the ring
-  {
-    const float* pr = probs + ((size_t)b * kH * N + i) * N;          // head h at pr + h * N * N
-    const float2* st2 = reinterpret_cast<const float2*>(stats) + (size_t)b * kH * N + i;
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < kH * N; idx += 128) {
-      const int h = idx / N, j = idx - h * N;
-      float v = __ldg(pr + (size_t)h * N * N + j);
-      if (stats) { const float2 st = __ldg(st2 + (size_t)h * N); v = exp2f(v - st.x) * st.y; }   // log-2 logits -> probabilities
-      A[j * kH + h] = v;
-    }
-  }
-  asm volatile("bar.sync 1, 128;" ::: "memory");                  // consumer warps only
-  float2 acc[kH][2];
-#pragma unroll
-  for (int h = 0; h < kH; ++h) acc[h][0] = acc[h][1] = make_float2(0.f, 0.f);
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c % kTmaStages;
-    mbar_wait_parity(full + s, (c / kTmaStages) & 1);
-    const float4* zc = reinterpret_cast<const float4*>(ring + (size_t)s * kTmaChunkFloats) + lane;
-    const int rows = min(kTmaRows, N - c * kTmaRows);
-#pragma unroll
-    for (int r4 = 0; r4 < kTmaRows / 4; ++r4) {
-      const int r = 4 * r4 + wid;
-      if (r < rows) {
-        const float4 zv = zc[r * (kCz / 4)];
-        const float4* ap = reinterpret_cast<const float4*>(A + (size_t)(c * kTmaRows + r) * kH);
-        float a[kH];
-#pragma unroll
-        for (int k = 0; k < kH / 4; ++k) { const float4 v = ap[k]; a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w; }
-        const float2 zlo = make_float2(zv.x, zv.y), zhi = make_float2(zv.z, zv.w);
-#pragma unroll
-        for (int h = 0; h < kH; ++h) {
-          const float2 aa = make_float2(a[h], a[h]);
-          acc[h][0] = __ffma2_rn(aa, zlo, acc[h][0]);
-          acc[h][1] = __ffma2_rn(aa, zhi, acc[h][1]);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(empty + s)) : "memory");
-  }
-  asm volatile("bar.sync 1, 128;" ::: "memory");                  // every chunk consumed: the ring is free for the reduction
-  float4* red = reinterpret_cast<float4*>(ring);                   // [4 warps][12][32 lanes] float4 = 24.6 KB <= 48 KB
-#pragma unroll
-  for (int h = 0; h < kH; ++h)
-    red[(wid * kH + h) * (kCz / 4) + lane] = make_float4(acc[h][0].x, acc[h][0].y, acc[h][1].x, acc[h][1].y);
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  float4* out = reinterpret_cast<float4*>(feats + ((size_t)b * N + i) * kFeat + kFeatPair);   // 'b i h c -> b i (h c)'
-  for (int o = threadIdx.x; o < kH * kCz / 4; o += 128) {
-    float4 sum = red[o];
-#pragma unroll
-    for (int w = 1; w < 4; ++w) {
-      const float4 v = red[w * kH * (kCz / 4) + o];
-      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-    }
-    out[o] = sum;
-  }
-}
-
 __host__ inline size_t agg_smem_bytes(int N) {
   size_t a = (size_t)N * kH, b = (size_t)kAggWarps * kH * kCz;
   return (a > b ? a : b) * sizeof(float);
@@ -829,9 +505,15 @@ __host__ inline size_t agg_smem_bytes(int N) {
 // ---------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-constexpr int kDefaultOverlapChunks = 0, kMaxOverlapChunks = 4;
-constexpr int kDefaultPrefetchMB = 64;   // measured on B200 (profiles/r01_ipa_pdl_ab.md): 0 -> 248 us, 32 -> 245, 64 -> 243, 96 -> 242 per B=8 layer-call
 constexpr int kMaxSplits = 8;   // split-K factor of the final projection (2112 -> 256) when B*N is small
+
+// fused path (ipa_fused.cu)
+size_t ipa_fused_qp_floats(int B, int N);
+size_t ipa_fused_kvp_floats(int B, int N);
+int launch_ipa_pack_nodes(cudaStream_t s, int B, int N, const float* proj, const float* rots, const float* trans, float* Qp,
+                          float* KVp);
+int launch_ipa_fused(cudaStream_t s, int B, int N, const float* Qp, const float* KVp, const float* bias, const float* mask,
+                     const float* rots, const float* trans, const float* point_weights, const float* z, float* feats);
 
 struct IpaWorkspace {
   float *proj, *Qdat, *Kdat, *Vdat, *probs, *stats, *feats, *bias, *partials;
@@ -846,6 +528,13 @@ static int final_proj_splits(int M) {
   return s < 1 ? 1 : (s > kMaxSplits ? kMaxSplits : s);
 }
 
+// ABX_IPA_FUSED=0 selects the round-1 two-kernel pipeline (tensor-core attention writing log-2 logits, then the
+// pair-aggregation stream) for A/B measurements at N <= 640; default: the fused kernel of ipa_fused.cu.
+static bool ipa_fused() {
+  static bool v = [] { const char* e = getenv("ABX_IPA_FUSED"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_feats) {
   IpaWorkspace w;
   size_t off = 0;
@@ -853,10 +542,10 @@ static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_fe
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(p + off); off += align_up(floats * sizeof(float)); return r; };
   const size_t bn = (size_t)B * N;
   w.proj = take(bn * kProj);
-  w.Qdat = take(bn * kH * kQK);
-  w.Kdat = take(bn * kH * kQK);
+  w.Qdat = take(bn * kH * kQK);                          // fused path: packed queries [B,N,12,28]
+  w.Kdat = take(bn * kH * (kQK + kVD));                  // fused path: packed keys + values [B,N,816]; else keys [B,H,N,28]
   w.Vdat = take(bn * kH * kVD);
-  w.probs = take(bn * kH * N);
+  w.probs = ipa_fused() ? nullptr : take(bn * kH * N);
   w.stats = take(bn * kH * 2);
   w.feats = with_feats ? take(bn * kFeat) : nullptr;
   w.partials = (with_feats && final_proj_splits((int)bn) > 1) ? take((size_t)final_proj_splits((int)bn) * bn * kC) : nullptr;
@@ -865,32 +554,11 @@ static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_fe
   return w;
 }
 
-// ABX_IPA_ATTENTION=simt selects the SIMT attention kernel (A/B measurements); default: tensor-core kernel
-static int attention_impl() {
-  static int v = [] { const char* e = getenv("ABX_IPA_ATTENTION"); return (e && e[0] == 's') ? 1 : 0; }();
-  return v;
-}
-
-// ABX_IPA_AGGREGATE=tma selects the bulk-copy (TMA) ring version of the pair aggregation kernel.  Measured on
-// B200 at N=350: register-streaming kernel 55.7 us (B=4) / 109 us (B=8), TMA ring 72 / 128 us — the ring's
-// per-chunk barrier round trips cost more than the deeper copy queue gains, so register streaming is the default.
-static int aggregate_impl() {
-  static int v = [] { const char* e = getenv("ABX_IPA_AGGREGATE"); return (e && e[0] == 't') ? 0 : 1; }();
-  return v;
-}
-
 // ABX_IPA_PDL=0 launches the kernels of a layer-call the ordinary way; default: programmatic dependent launch,
-// every kernel of the chain (node GEMM, pack, attention, pair aggregation, final projection, finalize) may start
+// every kernel of the chain (node GEMM, pack, fused attention, final projection, finalize) may start
 // while its predecessor drains and executes griddep_wait() before touching memory.
 static bool ipa_pdl() {
   static bool v = [] { const char* e = getenv("ABX_IPA_PDL"); return !(e && e[0] == '0'); }();
-  return v;
-}
-
-// ABX_IPA_PREFETCH_MB=<n>: the attention kernel warms L2 with the first n MB of z for the aggregation kernel
-// that follows it (0 = off).
-static size_t ipa_prefetch_bytes() {
-  static size_t v = [] { const char* e = getenv("ABX_IPA_PREFETCH_MB"); return (size_t)(e ? atoi(e) : kDefaultPrefetchMB) << 20; }();
   return v;
 }
 
@@ -911,44 +579,6 @@ struct PdlScope {
     if (int rc__ = check_launch(name)) return rc__;                                          \
   } while (0)
 
-// ABX_IPA_OVERLAP=<c> (2..4): software pipeline inside a layer-call.  The batch is cut into c chunks; the attention
-// kernel of chunk k+1 (tensor-pipe / latency bound, DRAM nearly idle) runs on a high-priority side stream while the
-// pair aggregation of chunk k (HBM bound) runs on the caller's stream.  Fork / join are events, so the pattern is
-// legal under stream capture.  0 / unset = one attention and one aggregation launch for the whole batch.
-static int ipa_overlap_chunks() {
-  const char* e = getenv("ABX_IPA_OVERLAP");
-  const int v = e ? atoi(e) : kDefaultOverlapChunks;
-  return v < 2 ? 1 : (v > kMaxOverlapChunks ? kMaxOverlapChunks : v);
-}
-
-struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, done[kMaxOverlapChunks] = {};
-  bool ready = false;
-};
-
-// Per-device side stream + events, created on the first call that is not being captured (resource creation is not
-// allowed while a capture in global mode is under way); nullptr = not available for this call.
-static SideStream* side_stream(cudaStream_t main_stream) {
-  static SideStream pool[64];
-  static std::mutex mu;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  SideStream& ss = pool[dev];
-  if (ss.ready) return &ss;
-  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(main_stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
-  int least = 0, greatest = 0;
-  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return nullptr;
-  if (cudaStreamCreateWithPriority(&ss.stream, cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
-  bool ok = cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess;
-  for (int k = 0; k < kMaxOverlapChunks && ok; ++k) ok = cudaEventCreateWithFlags(&ss.done[k], cudaEventDisableTiming) == cudaSuccess;
-  if (!ok) { cudaGetLastError(); return nullptr; }
-  ss.ready = true;
-  return &ss;
-}
-
 static int ipa_features(cudaStream_t s, int B, int N, const float* x, const float* z, const float* mask,
                         const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
                         float* feats, const IpaWorkspace& ws) {
@@ -960,78 +590,35 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
   if (w->w_proj_cat) {
     if ((rc = launch_linear_f32(s, M, kProj, kC, x, kC, w->w_proj_cat, w->b_proj_cat, nullptr, 0, ws.proj, kProj))) return rc;
   } else {
-  if ((rc = launch_linear_f32(s, M, kH * kSqk, kC, x, kC, w->w_q_scalar, w->b_q_scalar, nullptr, 0, ws.proj, kProj))) return rc;
-  if ((rc = launch_linear_f32(s, M, kH * (kSqk + kSv), kC, x, kC, w->w_kv_scalar, w->b_kv_scalar, nullptr, 0, ws.proj + kOffKV, kProj))) return rc;
-  if ((rc = launch_linear_f32(s, M, 3 * kH * kPqk, kC, x, kC, w->w_q_point, w->b_q_point, nullptr, 0, ws.proj + kOffQP, kProj))) return rc;
-  if ((rc = launch_linear_f32(s, M, 3 * kH * (kPqk + kPv), kC, x, kC, w->w_kv_point, w->b_kv_point, nullptr, 0, ws.proj + kOffKVP, kProj))) return rc;
+    if ((rc = launch_linear_f32(s, M, kH * kSqk, kC, x, kC, w->w_q_scalar, w->b_q_scalar, nullptr, 0, ws.proj, kProj))) return rc;
+    if ((rc = launch_linear_f32(s, M, kH * (kSqk + kSv), kC, x, kC, w->w_kv_scalar, w->b_kv_scalar, nullptr, 0, ws.proj + kOffKV, kProj))) return rc;
+    if ((rc = launch_linear_f32(s, M, 3 * kH * kPqk, kC, x, kC, w->w_q_point, w->b_q_point, nullptr, 0, ws.proj + kOffQP, kProj))) return rc;
+    if ((rc = launch_linear_f32(s, M, 3 * kH * (kPqk + kPv), kC, x, kC, w->w_kv_point, w->b_kv_point, nullptr, 0, ws.proj + kOffKVP, kProj))) return rc;
   }
-  ABX_LAUNCH("ipa_pack_kernel", ipa_pack_kernel, dim3(ceil_div(M * kH * kPackItems, 256)), dim3(256), 0, s, B, N, ws.proj, rots,
-             trans, ws.Qdat, ws.Kdat, ws.Vdat);
-
   if (pair_bias == nullptr) {
+    PdlScope plain(false);
     ipa_pair_bias_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), 256, 0, s>>>(N, z, w->w_pair, w->b_pair, ws.bias);
     count_launch();
     if ((rc = check_launch("ipa_pair_bias_kernel"))) return rc;
     pair_bias = ws.bias;
   }
 
-  const float* agg_stats = nullptr;          // non-null: `probs` holds log-2 logits to be normalised with (max, 1/sum)
   const size_t msmem = attn_mma_smem_floats(N) * sizeof(float);
-  if (attention_impl() == 0 && msmem <= 227 * 1024) {
-    ABX_CUDA(cudaFuncSetAttribute(ipa_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    const int chunks = aggregate_impl() == 1 ? (ipa_overlap_chunks() < B ? ipa_overlap_chunks() : B) : 1;
-    SideStream* ss = chunks > 1 ? side_stream(s) : nullptr;
-    if (ss) {
-      // attention of chunk k+1 on the side stream || aggregation of chunk k on the caller's stream
-      PdlScope plain(false);                       // event edges only between the two streams
-      const size_t gsmem = agg_smem_bytes(N);
-      ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-      ABX_CUDA(cudaEventRecord(ss->fork, s));
-      ABX_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-      const size_t n1 = (size_t)N, hnn = (size_t)kH * N * N;
-      int b0 = 0;
-      for (int k = 0; k < chunks; ++k) {
-        const int nb = (B - b0) / (chunks - k);    // even split, larger chunks last
-        const size_t zoff = (size_t)b0 * n1 * n1 * kCz, zbytes = (size_t)nb * n1 * n1 * kCz * sizeof(float);
-        const size_t pfb = k == 0 ? (ipa_prefetch_bytes() < zbytes ? ipa_prefetch_bytes() : zbytes) : 0;
-        ABX_LAUNCH("ipa_attention_mma_kernel", ipa_attention_mma_kernel, dim3(ceil_div(N, 16 * kMW), kH, nb), dim3(kMW * 32), msmem,
-                   ss->stream, N, ws.Qdat + (size_t)b0 * kH * n1 * kQK, ws.Kdat + (size_t)b0 * kH * n1 * kQK,
-                   ws.Vdat + (size_t)b0 * kH * n1 * kVD, pair_bias + b0 * hnn, mask + (size_t)b0 * n1, rots + (size_t)b0 * n1 * 9,
-                   trans + (size_t)b0 * n1 * 3, w->point_weights, ws.probs + b0 * hnn, ws.stats + (size_t)b0 * kH * n1 * 2,
-                   feats + (size_t)b0 * n1 * kFeat, reinterpret_cast<const char*>(z + zoff), (unsigned)(pfb / kPfChunk));
-        ABX_CUDA(cudaEventRecord(ss->done[k], ss->stream));
-        ABX_CUDA(cudaStreamWaitEvent(s, ss->done[k], 0));
-        ABX_LAUNCH("ipa_pair_aggregate_kernel", ipa_pair_aggregate_kernel, dim3(N, nb), dim3(kAggThreads), gsmem, s, N, z + zoff,
-                   ws.probs + b0 * hnn, ws.stats + (size_t)b0 * kH * n1 * 2, feats + (size_t)b0 * n1 * kFeat);
-        b0 += nb;
-      }
-      return ABX_OK;
-    }
-    const size_t zbytes = (size_t)B * N * N * kCz * sizeof(float);
-    const size_t pfb = aggregate_impl() == 1 ? (ipa_prefetch_bytes() < zbytes ? ipa_prefetch_bytes() : zbytes) : 0;
-    ABX_LAUNCH("ipa_attention_mma_kernel", ipa_attention_mma_kernel, dim3(ceil_div(N, 16 * kMW), kH, B), dim3(kMW * 32), msmem, s, N,
-               ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, ws.stats, feats,
-               reinterpret_cast<const char*>(z), (unsigned)(pfb / kPfChunk));
-    agg_stats = ws.stats;
-  } else {
-    const size_t asmem = attn_smem_bytes(N);
-    ABX_CUDA(cudaFuncSetAttribute(ipa_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
-    ipa_attention_kernel<<<dim3(ceil_div(N, kRows), kH, B), kAttnThreads, asmem, s>>>(
-        N, ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, feats);
-    count_launch();
-    if ((rc = check_launch("ipa_attention_kernel"))) return rc;
+  if (ipa_fused() || msmem > 227 * 1024) {
+    if ((rc = launch_ipa_pack_nodes(s, B, N, ws.proj, rots, trans, ws.Qdat, ws.Kdat))) return rc;
+    return launch_ipa_fused(s, B, N, ws.Qdat, ws.Kdat, pair_bias, mask, rots, trans, w->point_weights, z, feats);
   }
 
-  if (aggregate_impl() == 0) {
-    const size_t tsmem = agg_tma_smem_bytes(N);
-    ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-    ipa_pair_aggregate_tma_kernel<<<dim3(N, B), kTmaThreads, tsmem, s>>>(N, z, ws.probs, agg_stats, feats);
-    count_launch();
-    return check_launch("ipa_pair_aggregate_tma_kernel");
-  }
+  ABX_REQUIRE(ws.probs != nullptr, "ipa: the two-kernel path needs the probability workspace");
+  ABX_LAUNCH("ipa_pack_kernel", ipa_pack_kernel, dim3(ceil_div(M * kH * kPackItems, 256)), dim3(256), 0, s, B, N, ws.proj, rots,
+             trans, ws.Qdat, ws.Kdat, ws.Vdat);
+  ABX_CUDA(cudaFuncSetAttribute(ipa_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  ABX_LAUNCH("ipa_attention_mma_kernel", ipa_attention_mma_kernel, dim3(ceil_div(N, 16 * kMW), kH, B), dim3(kMW * 32), msmem, s, N,
+             ws.Qdat, ws.Kdat, ws.Vdat, pair_bias, mask, rots, trans, w->point_weights, ws.probs, ws.stats, feats,
+             reinterpret_cast<const char*>(z), 0u);
   const size_t gsmem = agg_smem_bytes(N);
   ABX_CUDA(cudaFuncSetAttribute(ipa_pair_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-  ABX_LAUNCH("ipa_pair_aggregate_kernel", ipa_pair_aggregate_kernel, dim3(N, B), dim3(kAggThreads), gsmem, s, N, z, ws.probs, agg_stats, feats);
+  ABX_LAUNCH("ipa_pair_aggregate_kernel", ipa_pair_aggregate_kernel, dim3(N, B), dim3(kAggThreads), gsmem, s, N, z, ws.probs, ws.stats, feats);
   return ABX_OK;
 }
 
