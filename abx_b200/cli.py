@@ -41,7 +41,11 @@ def build_parser(single_pdb):
     # additions
     p.add_argument('--samples_per_batch', type=int, default=8, help='independent samples of one complex batched per forward')
     p.add_argument('--num_t', type=int, default=None, help='override diffuser.inference_step')
-    p.add_argument('--seed', type=int, default=0, help='sample k is drawn with seed + k (independent of the GPU count)')
+    p.add_argument('--seed', type=int, default=0,
+                   help='base seed; each batch of samples draws from one generator seeded with a hash of (seed, sample '
+                        'indices of the batch), so results depend on --samples_per_batch and on the number of GPUs')
+    p.add_argument('--unsafe_pickle_checkpoint', action='store_true',
+                   help='load the checkpoint with torch.load(weights_only=False) (arbitrary unpickling; trusted files only)')
     p.add_argument('--no_cuda_graph', action='store_true')
     return p
 
@@ -57,7 +61,14 @@ def worker_load(args, device):
         config = json.load(f)
     config['diffuser']['so3']['use_cached_score'] = True                                   # inference.py:99
     if config['model']['embeddings_and_seqformer'].get('esm', {}).get('enabled'):
-        logging.warning('ESM2 conditioning needs fair-esm weights that are not available here: disabling esm.enabled')
+        if not args.model.startswith('random'):
+            raise RuntimeError(
+                f'{args.model_config} enables ESM2 conditioning (embeddings_and_seqformer.esm.enabled=true), which this '
+                'implementation does not provide (fair-esm and the esm2_t36_3B weights are not available offline). A '
+                'checkpoint trained with that config carries esm_embed_weights / proj_esm_embed parameters and would run '
+                'without the conditioning it was trained with. Use a checkpoint trained with esm.enabled=false together '
+                'with a config that says so.')
+        logging.warning('ESM2 conditioning is not supported: running the seeded random model with esm.enabled=false')
         config['model']['embeddings_and_seqformer']['esm']['enabled'] = False
     diffuser = FullDiffuser.get(config['diffuser'])
     model = ScoreNetwork(config['model'], diffuser)
@@ -66,7 +77,7 @@ def worker_load(args, device):
         load_seeded_(model, seed)
         logging.warning('running with seeded random weights (seed %d), not a trained checkpoint', seed)
     else:
-        ckpt = torch.load(args.model, map_location='cpu', weights_only=False)
+        ckpt = torch.load(args.model, map_location='cpu', weights_only=not getattr(args, 'unsafe_pickle_checkpoint', False))
         model.load_state_dict(ckpt['model_state_dict'], strict=True)                           # inference.py:105
     model = model.to(device).eval()
     optimize_steps = None
@@ -117,6 +128,11 @@ def run(args, raw_batches, rank=0, world=1):
     torch.cuda.set_device(device)
     feats, model, diffuser, config, optimize_steps = worker_load(args, device)
     num_t = args.num_t or config['diffuser']['inference_step']
+    if args.num_t:                                   # optimize mode derives its start time from inference_step (features.py:194-203)
+        config['diffuser']['inference_step'] = num_t
+        for name, kw in feats:
+            if name == 'make_diffuser_features':
+                kw['diff_conf'] = dict(kw['diff_conf'], inference_step=num_t)
     root = os.path.join(args.output_dir, args.mode)
     os.makedirs(root, exist_ok=True)
     plans = [(None, root)] if args.mode != 'optimize' else [(s, os.path.join(root, f'OPT-{s}')) for s in (optimize_steps or [])]
@@ -134,8 +150,9 @@ def run(args, raw_batches, rank=0, world=1):
             for c0 in range(0, len(mine), args.samples_per_batch):
                 ks = mine[c0:c0 + args.samples_per_batch]
                 t0 = time.time()
-                torch.manual_seed(args.seed + ks[0])
-                gen = torch.Generator(device=device).manual_seed(args.seed + ks[0])
+                chunk_seed = parallel.chunk_seed(args.seed, ks)
+                torch.manual_seed(chunk_seed)
+                gen = torch.Generator(device=device).manual_seed(chunk_seed)
                 batch = FeatureBuilder(fcfg).build(_repeat_batch(raw, len(ks)))
                 traj, final = sampler.sample_loop(batch, config, diffuser, model, mode=args.mode, num_t=num_t, generator=gen,
                                                   cuda_graph=not args.no_cuda_graph and args.mode != 'trajectory')

@@ -6,21 +6,24 @@
 // with the pair tensor z [B,N,N,128] read exactly once and no [B,H,N,N] logits / probability tensor.
 //
 // Work decomposition.  One CTA = a tile of R <= 20 consecutive query rows of one batch element, one warp per
-// query row, all 12 heads; the CTA walks the keys in chunks of 8:
-//   * z[b,i,:,:] (N x 512 B, contiguous) is streamed by the bulk-copy engine (cp.async.bulk, 2 KB pieces)
-//     into a warp-private 3-slot shared-memory ring guarded by mbarriers — the copies in flight (4 KB per
-//     warp, 80 KB per SM) do not occupy registers, and no cross-warp synchronisation touches the stream;
-//   * the packed key / value operands of the 8 keys (12 heads x (28 + 40) floats per key, 3264 B) are shared
-//     by the R rows of the tile: a double-buffered chunk filled by bulk copies (warp 0 issues them) and handed
-//     back through a count-R mbarrier;
-//   * per chunk each warp computes its row's 12 x 8 logits with lanes on (key, 3 heads) in exact fp32 SIMT
-//     arithmetic (packed FFMA2), runs an online softmax (running max / sum per head, accumulators rescaled
-//     only when a maximum moves), leaves the 8 x 12 probabilities in shared memory, accumulates the 480-wide
-//     value row (lane = float4 slices) and then the 12 x 128 pair row (lane = 4 channels, 24 FFMA2 per 16 bytes
-//     of z).
+// query row, all 12 heads; the CTA walks the keys in chunks of 8.  Everything the loop consumes arrives through
+// the bulk-copy engine (cp.async.bulk + mbarrier transaction counts), so no global load sits on a warp's
+// critical path and the bytes in flight do not occupy registers:
+//   * z[b,i,:,:] (N x 512 B, contiguous): 2 KB pieces into a warp-private 3-slot ring (4 KB in flight per warp,
+//     80 KB per SM), no cross-warp synchronisation;
+//   * the pair bias of row i, stored key-major [B,N,N,12] by ipa_pair_bias_kernel: one 384-byte copy per chunk
+//     into a warp-private double buffer, which then receives the chunk's probabilities in place;
+//   * the packed key / value operands of the 8 keys (per key 12 x (28 + 40) floats, the 12 key-side logit
+//     constants and the key mask: 3344 B), shared by the R rows of the tile: a double-buffered chunk filled by
+//     warp 0 and handed back through a count-R mbarrier.  The 126 MB L2 serves these re-reads at > 30 TB/s
+//     (tools/l2_probe.cu), so they do not compete with the HBM stream.
+// Per chunk each warp computes its row's 12 x 8 logits with lanes on (key, 3 heads) in exact fp32 SIMT arithmetic
+//   logit = [q_s, -2c Q] . [k_s, K] + c|Q|^2 + c|K|^2 + bias      (28-long packed FFMA2 dot product, c = -gamma_h w_point / 2)
+// runs an online softmax (running max / sum per head, accumulators rescaled only when a maximum moves), leaves the
+// 8 x 12 probabilities in shared memory, accumulates the 480-wide value row (lane = float4 slices) and then the
+// 12 x 128 pair row (lane = 4 channels, 24 FFMA2 per 16 bytes of z).
 // The tile height R is chosen on the host so that B * ceil(N / R) tiles fill the 148 SMs in whole rounds
-// (B = 8, N = 350: R = 20 -> 144 CTAs, one per SM); larger R also amortises the key / value chunk reads
-// (3264 B per key per tile against 512 B of z per key per row).
+// (B = 8, N = 350: R = 20 -> 144 CTAs, one per SM).
 #include <float.h>
 
 #include "common.cuh"

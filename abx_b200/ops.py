@@ -85,14 +85,26 @@ _CM_BUFFERS = {}
 
 
 def _cm_buffer(tag, shape, device):
-    """Zero-initialised channel-major scratch buffer, cached per (tag, shape, device): its pad columns are never
-    written, so they stay zero across calls."""
-    key = (tag, tuple(shape), str(device))
-    buf = _CM_BUFFERS.get(key)
-    if buf is None:
-        buf = torch.zeros(shape, device=device, dtype=torch.float32)
-        _CM_BUFFERS[key] = buf
-    return buf
+    """Zero-padded channel-major scratch: ONE grow-only flat buffer per (tag, device).  The kernels never write the
+    pad columns, which must read as zero, so the view is zero-filled whenever its shape differs from the previous
+    call's (the old contents would otherwise land in the new pad positions); with a steady shape nothing is cleared."""
+    key = (tag, str(device))
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    flat, last = _CM_BUFFERS.get(key, (None, None))
+    if flat is None or flat.numel() < numel:
+        flat, last = torch.zeros(numel, device=device, dtype=torch.float32), tuple(shape)
+    view = flat[:numel].view(*shape)
+    if last != tuple(shape):
+        view.zero_()
+    _CM_BUFFERS[key] = (flat, tuple(shape))
+    return view
+
+
+def release_scratch():
+    """Drop the cached scratch buffers (long runs over complexes of many sizes can return the memory)."""
+    _CM_BUFFERS.clear()
 
 
 def triangle_product(x, w_glu, b_glu, pair_mask, norm_weight, norm_bias, eps=1e-5):

@@ -11,9 +11,17 @@ import torch.distributed as dist
 
 
 def shard_samples(num_samples, rank, world):
-    """Indices of the samples rank `rank` designs (round-robin, so results do not depend on `world`
-    when sample k is seeded with `base_seed + k`)."""
+    """Indices of the samples rank `rank` designs (round-robin)."""
     return list(range(rank, num_samples, world))
+
+
+def chunk_seed(base_seed, sample_indices):
+    """Seed of the generator one batch of samples draws from: a stable hash of (base seed, the batch's sample
+    indices).  Different base seeds or different batches never share a seed; the draws of sample k depend on
+    which samples it is batched with (i.e. on --samples_per_batch and on the number of ranks)."""
+    import hashlib
+    h = hashlib.sha256(repr((int(base_seed), tuple(int(k) for k in sample_indices))).encode()).digest()
+    return int.from_bytes(h[:8], 'little') & 0x7FFFFFFFFFFFFFFF
 
 
 def _active(group=None):

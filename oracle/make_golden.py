@@ -460,8 +460,124 @@ def gen_sampler():
     save('sampler', **arrays, diffuse_mask=diffuse_mask, **out)
 
 
+def _to64(x):
+    if torch.is_tensor(x):
+        return x.double() if x.is_floating_point() else x
+    if isinstance(x, tuple):
+        return tuple(_to64(v) for v in x)
+    return x
+
+
+def _pair_digest(pair, pos):
+    """Compact check data of a [1,N,N,C] pair tensor: the channel vectors at sampled (i,j) positions plus the sums
+    over j, over i and over the diagonal band — any transposed / shifted / tile-local indexing error moves them."""
+    p = pair[0]
+    return dict(samples=p[pos[:, 0], pos[:, 1]], row_sum=p.sum(dim=1), col_sum=p.sum(dim=0))
+
+
+def gen_big(n_antigen, name):
+    """BASELINE-size parity data (N = 230 + n_antigen, B = 1, H3 diffused) with a float64 error budget:
+      r32_*  the REFERENCE's own modules in float32 (what the product must match),
+      o64_*  oracle/model.py evaluated in float64 on the same inputs and weights ("exact" value of the arithmetic),
+    for (a) one trunk pass from zero self-conditioning (seqformer.py:170-226), (b) IpaScore on seeded random
+    representations (score_network.py:83-196), (c) ScoreNetwork.forward (abx.py:75-104).  |r32 - o64| is the float32
+    noise of the reference itself; the GPU tests bound |product - o64| by a small multiple of it."""
+    from abx.model.features import FeatureBuilder
+    from abx.model.abx import get_prev
+    from abx_b200.data.synthetic import synthetic_complex
+    from abx_b200.utils.weights import np_randn
+    from oracle import model as OM
+    from oracle.diffusers import OracleDiffuser
+    model, cfg = _ref_model()
+    _, raw = ref_harness.load_config(cache_dir=CACHE)
+    fd = get_diffuser()
+    with open(os.path.join(ref_harness.REFERENCE_ROOT, 'config', 'config_data_feature.json')) as f:
+        feats = json.load(f)
+    for fname, args in feats:
+        if 'device' in args:
+            args['device'] = 'cpu'
+        if 'diffuse' in fname:
+            args['diff_conf'] = raw['diffuser']
+            args.pop('optimize_steps', None)
+            args['generate_area'] = 'H3'
+    torch.manual_seed(4000 + n_antigen)
+    batch = FeatureBuilder(feats, is_training=False).build(synthetic_complex(n_antigen=n_antigen, seed=3, batch_size=1))
+    batch['t'] = torch.tensor([0.6])
+    batch['is_recycling'] = False
+    arrays = _batch_arrays(batch)
+    B, N = batch['seq'].shape
+    pos = torch.from_numpy(np.random.default_rng(99).integers(0, N, size=(1536, 2)))
+    out = dict(arrays, pair_pos=pos)
+    P32 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    P64 = {k: _to64(v) for k, v in P32.items()}
+    od = OracleDiffuser(fd._so3_diffuser._score_norms, cdf=fd._so3_diffuser._cdf, pdf=None)
+
+    def zero_prev(b, dt):
+        b = dict(b)
+        b.update(prev_pos=torch.zeros(B, N, N, dtype=torch.int64), prev_seq=torch.zeros(B, N, 544, dtype=dt),
+                 prev_pair=torch.zeros(B, N, N, 192, dtype=dt), is_recycling=True)
+        return b
+
+    rep_seq, rep_pair = np_randn(921, B, N, 544), np_randn(922, B, N, N, 192)      # regenerated by the tests
+    t0 = time.time()
+    with torch.no_grad():
+        # ---- reference, float32
+        s32, p32 = model.impl.seqformer(zero_prev(batch, torch.float32))
+        ipa32 = model.impl.diffusion_module.ScoreNetwork({'seq': rep_seq, 'pair': rep_pair}, dict(batch))
+        bm = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        m32 = model(bm)
+        prev32 = get_prev(bm, m32, cfg.model)
+        print(f'  reference float32 done ({time.time() - t0:.0f}s)')
+        # ---- oracle, float64
+        OM.set_compute_dtype(torch.float64)
+        try:
+            b64 = {k: _to64(v) for k, v in batch.items()}
+            z = zero_prev(b64, torch.float64)
+            s64, p64 = OM.embed_inputs(P64, z)
+            s64, p64 = OM.seqformer_block(P64, s64, p64, z['mask'])
+            ipa64 = OM.ipascore_forward(P64, od, rep_seq.double(), rep_pair.double(), dict(b64))
+            bm64 = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in b64.items()}
+            m64 = OM.score_network(P64, od, bm64)
+        finally:
+            OM.set_compute_dtype(torch.float32)
+        print(f'  oracle float64 done ({time.time() - t0:.0f}s)')
+    h = m32['heads']
+    out.update(r32_trunk_seq=s32, o64_trunk_seq=s64.float())
+    out.update({'r32_trunk_pair_' + k: v for k, v in _pair_digest(p32, pos).items()})
+    out.update({'o64_trunk_pair_' + k: v.float() for k, v in _pair_digest(p64, pos).items()})
+    for tag, o in (('r32', ipa32), ('o64', ipa64)):
+        sm = o['representations']['structure_module'] if 'representations' in o else o['structure_module']
+        ang = o['sidechains'][-1]['angles_sin_cos'] if 'sidechains' in o else o['angles_sin_cos']
+        out.update({f'{tag}_ipa_structure_module': sm.float(), f'{tag}_ipa_rigids': o['rigids'].float(),
+                    f'{tag}_ipa_angles': ang.float(), f'{tag}_ipa_trans_score': o['trans_score'].float(),
+                    f'{tag}_ipa_rot_score': o['rot_score'].float()})
+    out.update(r32_rigids=h['folding']['rigids'], r32_atom14=h['folding']['final_atom14_positions'],
+               r32_trans_score=h['folding']['trans_score'], r32_rot_score=h['folding']['rot_score'],
+               r32_logits=h['sequence_module']['logits'], r32_seq_0=h['sequence_module']['seq_0'],
+               r32_pLDDT=h['predicted_lddt']['pLDDT'], r32_rep_seq=m32['representations']['seq'],
+               r32_seq_t_after=bm['seq_t'], r32_prev_pos=prev32['prev_pos'])
+    out.update({'r32_rep_pair_' + k: v for k, v in _pair_digest(m32['representations']['pair'], pos).items()})
+    out.update(o64_rigids=m64['rigids'].float(), o64_atom14=m64['atom14'].float(), o64_trans_score=m64['trans_score'].float(),
+               o64_rot_score=m64['rot_score'].float(), o64_logits=m64['logits'].float(), o64_seq_0=m64['seq_0'],
+               o64_pLDDT=m64['pLDDT'].float(), o64_rep_seq=m64['rep_seq'].float())
+    out.update({'o64_rep_pair_' + k: v.float() for k, v in _pair_digest(m64['rep_pair'], pos).items()})
+    for k in ('trunk_seq', 'rigids', 'atom14', 'trans_score', 'logits', 'pLDDT', 'rep_seq', 'ipa_structure_module', 'ipa_rigids'):
+        d = (out['r32_' + k].double() - out['o64_' + k].double()).abs().max()
+        print(f'  |reference32 - oracle64| {k:22s} {float(d):.3e}   (scale {float(out["o64_" + k].abs().max()):.3g})')
+    save(name, **out)
+
+
+def gen_model_n350():
+    gen_big(120, 'model_n350')
+
+
+def gen_model_n262():
+    gen_big(32, 'model_n262')
+
+
 ALL = dict(geometry=gen_geometry, igso3=gen_igso3, scores=gen_scores, reverse=gen_reverse, reverse_edges=gen_reverse_edges, prior=gen_prior, marginal=gen_marginal,
-           ipa=gen_ipa, ipascore=gen_ipascore, model=gen_model, sampler=gen_sampler)
+           ipa=gen_ipa, ipascore=gen_ipascore, model=gen_model, sampler=gen_sampler,
+           model_n350=gen_model_n350, model_n262=gen_model_n262)
 
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)

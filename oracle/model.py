@@ -24,6 +24,18 @@ MODEL_CONF = dict(num_recycle=2, seq_channel=512, pair_channel=128, max_relative
 SN = 'impl.diffusion_module.ScoreNetwork.'
 TR = 'impl.seqformer.'
 
+# Working dtype of the activations.  float32 restates the reference; float64 (set_compute_dtype) gives the
+# "true" value of the same arithmetic, against which the float32 noise of the reference, of this oracle and of
+# the CUDA path is measured (oracle/make_golden.py gen_big, tests/test_gpu_model.py error budgets).
+DTYPE = torch.float32
+
+
+def set_compute_dtype(dtype):
+    """torch.float32 (reference semantics) or torch.float64 (error-budget runs: pass float64 params and inputs)."""
+    global DTYPE
+    assert dtype in (torch.float32, torch.float64)
+    DTYPE = dtype
+
 
 def linear(P, name, x):
     b = P.get(name + '.bias')
@@ -97,7 +109,7 @@ def torsion_module(P, prefix, act, init_act):
 
 def torsion_angles_to_frames(aatype, rots, trans, sin_cos):
     """atom.py:9-58: 8 rigid groups per residue in the global frame."""
-    m = torch.from_numpy(rt.table('restype_rigid_group_default_frame'))[aatype]            # [B,N,8,4,4]
+    m = torch.from_numpy(rt.table('restype_rigid_group_default_frame')).to(aatype.device)[aatype].to(sin_cos.dtype)           # [B,N,8,4,4]
     d_rot, d_trans = m[..., :3, :3], m[..., :3, 3]
     sin = F.pad(sin_cos[..., 0], (1, 0), value=0.)
     cos = F.pad(sin_cos[..., 1], (1, 0), value=1.)
@@ -118,10 +130,10 @@ def torsion_angles_to_frames(aatype, rots, trans, sin_cos):
 def frames_to_atom14(aatype, frames):
     """atom.py:60-76."""
     f_rot, f_trans = frames
-    grp = torch.from_numpy(rt.table('restype_atom14_to_rigid_group'))[aatype].long()       # [B,N,14]
+    grp = torch.from_numpy(rt.table('restype_atom14_to_rigid_group')).to(aatype.device)[aatype].long()       # [B,N,14]
     a_rot = torch.gather(f_rot, 2, grp[..., None, None].expand(grp.shape + (3, 3)))
     a_trans = torch.gather(f_trans, 2, grp[..., None].expand(grp.shape + (3,)))
-    lit = torch.from_numpy(rt.table('restype_atom14_rigid_group_positions'))[aatype]
+    lit = torch.from_numpy(rt.table('restype_atom14_rigid_group_positions')).to(aatype.device)[aatype]
     return a_trans + torch.einsum('...rd,...d->...r', a_rot, lit)
 
 
@@ -131,14 +143,14 @@ def frames_to_atom14(aatype, frames):
 
 def ipascore_forward(P, diffuser, rep_seq, rep_pair, batch, c=IPA_CONF):
     seq = batch['seq_t']
-    node_mask = batch['mask'].float()
+    node_mask = batch['mask'].to(DTYPE)
     fixed = batch['fixed_mask']
-    init_rigids = batch['rigids_t'].float()                                                 # :90
+    init_rigids = batch['rigids_t'].to(DTYPE)                                               # :90
     init_q, init_t = init_rigids[..., :4], init_rigids[..., 4:]
     scale = c['position_scale']
     B, N = seq.shape
 
-    delta_q = torch.cat([torch.ones(B, N, 1), torch.zeros(B, N, 3)], dim=-1)               # make_identity :107
+    delta_q = torch.cat([torch.ones(B, N, 1, dtype=DTYPE, device=seq.device), torch.zeros(B, N, 3, dtype=DTYPE, device=seq.device)], dim=-1)               # make_identity :107
     cur_q, cur_t = init_q, init_t / scale
     cur_R = Q.quat_to_rot(cur_q)
 
@@ -281,8 +293,8 @@ def timestep_embedding(t, dim, max_positions=10000):
     t = t * max_positions
     half = dim // 2
     e = math.log(max_positions) / (half - 1)
-    e = torch.exp(torch.arange(half, dtype=torch.float32) * -e)
-    e = t.float()[:, None] * e[None, :]
+    e = torch.exp(torch.arange(half, dtype=DTYPE) * -e)
+    e = t.to(DTYPE)[:, None] * e[None, :]
     return torch.cat([torch.sin(e), torch.cos(e)], dim=1)
 
 
@@ -305,15 +317,15 @@ def embed_inputs(P, batch, mc=MODEL_CONF):
     ag_pair = P[TR + 'proj_rel_pos.weight'][relpos(batch['residx'][:, n_ab:])]
 
     seq_act = torch.cat([ab_seq, ag_seq], dim=1)
-    pair_act = torch.zeros(B, N, N, ab_pair.shape[-1])                                      # pair_concat :24-45
+    pair_act = torch.zeros(B, N, N, ab_pair.shape[-1], dtype=ab_pair.dtype)                                    # pair_concat :24-45
     pair_act[:, :n_ab, :n_ab] = ab_pair
     pair_act[:, n_ab:, n_ab:] = ag_pair
     seq_act = seq_act + residue_embedding(P, batch)
     pair_act = pair_act + pair_embedding(P, batch, mc['prev_pos'])
 
     te = timestep_embedding(batch['t'], mc['index_embed_size'])[:, None, :].expand(B, N, -1)   # Embedder :93-119
-    seq_act = torch.cat([seq_act, te], dim=-1).float()
-    pair_act = torch.cat([pair_act, te[:, :, None, :].expand(B, N, N, -1), te[:, None, :, :].expand(B, N, N, -1)], dim=-1).float()
+    seq_act = torch.cat([seq_act, te], dim=-1).to(DTYPE)
+    pair_act = torch.cat([pair_act, te[:, :, None, :].expand(B, N, N, -1), te[:, None, :, :].expand(B, N, N, -1)], dim=-1).to(DTYPE)
 
     seq_act = seq_act + layer_norm(P, TR + 'prev_seq_norm', batch['prev_seq'])              # :213-217
     pair_act = pair_act + layer_norm(P, TR + 'prev_pair_norm', batch['prev_pair'])
@@ -429,8 +441,9 @@ def score_network(P, diffuser, batch, mc=MODEL_CONF):
     quirk — seq_t <- the recycle's predicted seq_0 (:97-98)."""
     B, N = batch['seq'].shape
     if 'prev_seq' not in batch:
-        batch.update(prev_pos=torch.zeros(B, N, N, dtype=torch.int64), prev_seq=torch.zeros(B, N, 544),
-                     prev_pair=torch.zeros(B, N, N, 192))
+        dev = batch['seq_t'].device
+        batch.update(prev_pos=torch.zeros(B, N, N, dtype=torch.int64, device=dev), prev_seq=torch.zeros(B, N, 544, dtype=DTYPE, device=dev),
+                     prev_pair=torch.zeros(B, N, N, 192, dtype=DTYPE, device=dev))
     with torch.no_grad():
         for _ in range(mc['num_recycle']):
             out = iteration(P, diffuser, batch, with_plddt=False)
