@@ -7,12 +7,13 @@
 //                                rigid transform, norms: the 2112-wide feature row                   :79-128
 //   node GEMM (split-K)          final_proj over the feature row (+ bias + residual)                 :130-132
 //
-//   ipa_pair_bias_kernel         sqrt(1/3) (z W_pair^T + b), head-major [B,H,N,N]: depends on z and the weights
-//                                only, so IpaScore evaluates it once for its 8 weight-shared iterations :101-104
+//   ipa_pair_bias_chunked_kernel sqrt(1/3) (z W_pair^T + b) in the chunked key-major layout the fused kernel streams
+//   (ipa_fused.cu)               ([B, ceil(N/8), N, 100]): depends on z and the weights only, so IpaScore evaluates
+//                                it once for its 8 weight-shared iterations                          :101-104
 //
 // The round-1 two-kernel core (tensor-core attention writing log-2 logits + pair-aggregation stream) is kept
 // behind ABX_IPA_FUSED=0 for A/B measurements.
-// Data layout (all fp32): z [B,N,N,128] row-major as the reference holds it; pair bias head-major [B,H,N,N].
+// Data layout (all fp32): z [B,N,N,128] row-major as the reference holds it.
 #include <float.h>
 #include <stdlib.h>
 
@@ -510,6 +511,8 @@ constexpr int kMaxSplits = 8;   // split-K factor of the final projection (2112 
 // fused path (ipa_fused.cu)
 size_t ipa_fused_qp_floats(int B, int N);
 size_t ipa_fused_kvp_floats(int B, int N);
+size_t ipa_pair_bias_floats(int B, int N);
+int launch_ipa_pair_bias(cudaStream_t s, int B, int N, const float* z, const float* w_pair, const float* b_pair, float* bias);
 int launch_ipa_pack_nodes(cudaStream_t s, int B, int N, const float* proj, const float* rots, const float* trans, float* Qp,
                           float* KVp);
 int launch_ipa_fused(cudaStream_t s, int B, int N, const float* Qp, const float* KVp, const float* bias, const float* mask,
@@ -549,7 +552,10 @@ static IpaWorkspace carve(void* base, int B, int N, bool with_bias, bool with_fe
   w.stats = take(bn * kH * 2);
   w.feats = with_feats ? take(bn * kFeat) : nullptr;
   w.partials = (with_feats && final_proj_splits((int)bn) > 1) ? take((size_t)final_proj_splits((int)bn) * bn * kC) : nullptr;
-  w.bias = with_bias ? take(bn * kH * N) : nullptr;
+  {
+    const size_t head_major = bn * kH * N, chunked = ipa_pair_bias_floats(B, N);
+    w.bias = with_bias ? take(head_major > chunked ? head_major : chunked) : nullptr;
+  }
   w.total = off;
   return w;
 }
@@ -595,21 +601,26 @@ static int ipa_features(cudaStream_t s, int B, int N, const float* x, const floa
     if ((rc = launch_linear_f32(s, M, 3 * kH * kPqk, kC, x, kC, w->w_q_point, w->b_q_point, nullptr, 0, ws.proj + kOffQP, kProj))) return rc;
     if ((rc = launch_linear_f32(s, M, 3 * kH * (kPqk + kPv), kC, x, kC, w->w_kv_point, w->b_kv_point, nullptr, 0, ws.proj + kOffKVP, kProj))) return rc;
   }
-  if (pair_bias == nullptr) {
+  const size_t msmem = attn_mma_smem_floats(N) * sizeof(float);
+  if (ipa_fused() || msmem > 227 * 1024) {
+    if (pair_bias == nullptr) {
+      ABX_REQUIRE(ws.bias != nullptr, "ipa: no pair bias and no workspace room for it");
+      if ((rc = launch_ipa_pair_bias(s, B, N, z, w->w_pair, w->b_pair, ws.bias))) return rc;
+      pair_bias = ws.bias;
+    }
+    if ((rc = launch_ipa_pack_nodes(s, B, N, ws.proj, rots, trans, ws.Qdat, ws.Kdat))) return rc;
+    return launch_ipa_fused(s, B, N, ws.Qdat, ws.Kdat, pair_bias, mask, rots, trans, w->point_weights, z, feats);
+  }
+
+  // round-1 two-kernel path (A/B only): it reads a head-major bias, which it always evaluates itself
+  ABX_REQUIRE(ws.probs != nullptr && ws.bias != nullptr, "ipa: the two-kernel path needs the probability and bias workspace");
+  {
     PdlScope plain(false);
     ipa_pair_bias_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), 256, 0, s>>>(N, z, w->w_pair, w->b_pair, ws.bias);
     count_launch();
     if ((rc = check_launch("ipa_pair_bias_kernel"))) return rc;
     pair_bias = ws.bias;
   }
-
-  const size_t msmem = attn_mma_smem_floats(N) * sizeof(float);
-  if (ipa_fused() || msmem > 227 * 1024) {
-    if ((rc = launch_ipa_pack_nodes(s, B, N, ws.proj, rots, trans, ws.Qdat, ws.Kdat))) return rc;
-    return launch_ipa_fused(s, B, N, ws.Qdat, ws.Kdat, pair_bias, mask, rots, trans, w->point_weights, z, feats);
-  }
-
-  ABX_REQUIRE(ws.probs != nullptr, "ipa: the two-kernel path needs the probability workspace");
   ABX_LAUNCH("ipa_pack_kernel", ipa_pack_kernel, dim3(ceil_div(M * kH * kPackItems, 256)), dim3(256), 0, s, B, N, ws.proj, rots,
              trans, ws.Qdat, ws.Kdat, ws.Vdat);
   ABX_CUDA(cudaFuncSetAttribute(ipa_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
@@ -659,13 +670,17 @@ extern "C" size_t abx_ipa_workspace_bytes(int B, int N) {
   return carve(nullptr, B, N, true, true).total;
 }
 
+extern "C" size_t abx_ipa_pair_bias_floats(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  return ipa_pair_bias_floats(B, N);
+}
+
 extern "C" int abx_ipa_pair_bias(void* stream, int B, int N, const float* z, const float* w_pair, const float* b_pair,
                                  float* pair_bias) {
   ABX_REQUIRE(B > 0 && N > 0 && z && w_pair && b_pair && pair_bias, "abx_ipa_pair_bias: bad shape or null argument");
-  ABX_REQUIRE((uintptr_t)z % 16 == 0 && (uintptr_t)w_pair % 16 == 0, "abx_ipa_pair_bias: z and w_pair must be 16-byte aligned");
-  ipa_pair_bias_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), 256, 0, (cudaStream_t)stream>>>(N, z, w_pair, b_pair, pair_bias);
-  count_launch();
-  return check_launch("ipa_pair_bias_kernel");
+  ABX_REQUIRE((uintptr_t)z % 16 == 0 && (uintptr_t)w_pair % 16 == 0 && (uintptr_t)pair_bias % 16 == 0,
+              "abx_ipa_pair_bias: z, w_pair and pair_bias must be 16-byte aligned");
+  return launch_ipa_pair_bias((cudaStream_t)stream, B, N, z, w_pair, b_pair, pair_bias);
 }
 
 extern "C" int abx_ipa_attention_features(void* stream, int B, int N, const float* x, const float* z, const float* mask,
@@ -674,7 +689,7 @@ extern "C" int abx_ipa_attention_features(void* stream, int B, int N, const floa
   int rc = ipa_check("abx_ipa_attention_features", B, N, x, z, mask, rots, trans, w);
   if (rc) return rc;
   ABX_REQUIRE(feats && workspace, "abx_ipa_attention_features: null output or workspace");
-  IpaWorkspace ws = carve(workspace, B, N, pair_bias == nullptr, false);
+  IpaWorkspace ws = carve(workspace, B, N, pair_bias == nullptr || !ipa_fused(), false);
   ABX_REQUIRE(workspace_bytes >= ws.total, "abx_ipa_attention_features: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
   return ipa_features((cudaStream_t)stream, B, N, x, z, mask, rots, trans, w, pair_bias, feats, ws);
 }
@@ -685,7 +700,7 @@ extern "C" int abx_ipa_forward(void* stream, int B, int N, const float* x, const
   int rc = ipa_check("abx_ipa_forward", B, N, x, z, mask, rots, trans, w);
   if (rc) return rc;
   ABX_REQUIRE(out && workspace, "abx_ipa_forward: null output or workspace");
-  IpaWorkspace ws = carve(workspace, B, N, pair_bias == nullptr, true);
+  IpaWorkspace ws = carve(workspace, B, N, pair_bias == nullptr || !ipa_fused(), true);
   ABX_REQUIRE(workspace_bytes >= ws.total, "abx_ipa_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
   cudaStream_t s = (cudaStream_t)stream;
   PdlScope pdl(ipa_pdl());

@@ -1,29 +1,34 @@
-// Fused Invariant Point Attention core (abx/model/folding.py:79-128) — ONE kernel for
+// Fused Invariant Point Attention core (abx/model/folding.py:79-128) — ONE warp-specialised kernel for
 //   logits (scalar q.k + point distances + pair bias, mask)  :79-109
 //   softmax over the keys                                     :110
 //   attention over scalar / point values, inverse rigid transform, point norms   :114-123
 //   attention over the pair activations  o_pair[i,h,:] = sum_j a[h,i,j] z[i,j,:]  :126-127
 // with the pair tensor z [B,N,N,128] read exactly once and no [B,H,N,N] logits / probability tensor.
 //
-// Work decomposition.  One CTA = a tile of R <= 20 consecutive query rows of one batch element, one warp per
-// query row, all 12 heads; the CTA walks the keys in chunks of 8.  Everything the loop consumes arrives through
-// the bulk-copy engine (cp.async.bulk + mbarrier transaction counts), so no global load sits on a warp's
-// critical path and the bytes in flight do not occupy registers:
-//   * z[b,i,:,:] (N x 512 B, contiguous): 2 KB pieces into a warp-private 3-slot ring (4 KB in flight per warp,
-//     80 KB per SM), no cross-warp synchronisation;
-//   * the pair bias of row i, stored key-major [B,N,N,12] by ipa_pair_bias_kernel: one 384-byte copy per chunk
-//     into a warp-private double buffer, which then receives the chunk's probabilities in place;
-//   * the packed key / value operands of the 8 keys (per key 12 x (28 + 40) floats, the 12 key-side logit
-//     constants and the key mask: 3344 B), shared by the R rows of the tile: a double-buffered chunk filled by
-//     warp 0 and handed back through a count-R mbarrier.  The 126 MB L2 serves these re-reads at > 30 TB/s
-//     (tools/l2_probe.cu), so they do not compete with the HBM stream.
-// Per chunk each warp computes its row's 12 x 8 logits with lanes on (key, 3 heads) in exact fp32 SIMT arithmetic
-//   logit = [q_s, -2c Q] . [k_s, K] + c|Q|^2 + c|K|^2 + bias      (28-long packed FFMA2 dot product, c = -gamma_h w_point / 2)
-// runs an online softmax (running max / sum per head, accumulators rescaled only when a maximum moves), leaves the
-// 8 x 12 probabilities in shared memory, accumulates the 480-wide value row (lane = float4 slices) and then the
-// 12 x 128 pair row (lane = 4 channels, 24 FFMA2 per 16 bytes of z).
-// The tile height R is chosen on the host so that B * ceil(N / R) tiles fill the 148 SMs in whole rounds
-// (B = 8, N = 350: R = 20 -> 144 CTAs, one per SM).
+// The O(N^2 Cz) part — 1536 of the ~2350 multiply-adds per (query, key) pair — does not fit the fp32 SIMT pipe at
+// HBM speed (6 flop per z byte), so it runs on the 5th-generation tensor cores as 3xTF32 (fp32-level accuracy):
+//     D_i[c, h] += sum_k z[i, j0+k, c] * p[h, i, j0+k]        M = 128 channels, N = 16 (12 heads), K = 8 keys
+// with A = z in TENSOR MEMORY (lane = channel, column = key; hi = the raw fp32 word — the tensor core ignores the 13 low
+// mantissa bits — and lo = z - hi, written with tcgen05.st), B = the chunk's probabilities (hi / lo tiles in shared
+// memory, K-major, no swizzle) and the accumulator D_i in tensor memory (16 columns per query row).
+//
+// One CTA (28 warps, register budgets re-balanced with setmaxnreg) = a tile of R <= 20 query rows of one batch
+// element; it walks the keys in chunks of 8 with every row in lock step, so the chunk's packed key / value operands
+// (26 KB, one bulk copy, served by L2) are shared by the R rows.  Roles:
+//   warp 0        z producer: one 4 KB cp.async.bulk per (row, chunk) "item" into a shared-memory ring (mbarrier tx counts)
+//   warp 2        key/value + pair-bias producer (double-buffered chunk, two bulk copies)
+//   warps 4-11    two converter warpgroups (alternating items): thread = channel reads the item's 8 keys, splits hi / lo,
+//                 tcgen05.st into a 12-slot A ring in tensor memory, releases the z slot
+//   warps 16-19   logits + online softmax: thread = (head, 2 query rows) with its queries in registers, all 8 keys of the
+//                 chunk; exact fp32 FFMA2 arithmetic.  The softmax reference point m is fixed by the first chunk and only
+//                 moves when a later logit exceeds it by 2^64 (flagged, see below), so accumulators are never rescaled in
+//                 the common case.  Writes p (hi / lo MMA operand tiles + a plain copy for the value warps).
+//   warps 20-27   attention over the 40-wide value rows: thread = (10 query rows x 4 value dims) register tile
+//   warp 1        MMA issuer: per item 3 x tcgen05.mma (hi*lo, lo*hi, hi*hi), commit -> frees the A slot
+//   warps 12-15   accumulator service: rescales D_i in tensor memory when a reference point moved (rare), and at the end
+//                 reads D (tcgen05.ld), normalises by the row sums and writes o_pair
+// The pair bias sqrt(1/3)(z W^T + b) is read from the chunked key-major tensor written by ipa_pair_bias_kernel
+// ([B, ceil(N/8), N, 100]: row i of chunk c holds bias[j0+k][h] at 12 k + h): one 8 KB bulk copy per chunk and tile.
 #include <float.h>
 
 #include "common.cuh"
@@ -39,19 +44,48 @@ constexpr int kVD = kSv + 3 * kPv;            // 40: value operand per head
 constexpr int kQRow = kH * kQK;               // 336 floats per residue: packed queries
 constexpr int kVOff = kH * kQK;               // values follow the keys inside a packed key/value row
 constexpr int kKVRow = kH * (kQK + kVD);      // 816 floats per residue: packed keys + values
-constexpr int kKVStride = kKVRow + 4;         // shared-memory row stride: conflict-free float4 reads with lanes on keys
-constexpr int kChunk = 8;                     // keys per key/value chunk
-constexpr int kZKeys = 4, kZSlots = 3;        // z ring: 3 slots of 4 keys (2 KB) per warp
-constexpr int kZSlotFloats = kZKeys * kCz;
-constexpr int kMaxRows = 20;                  // query rows (= warps) per CTA
-constexpr int kStatFloats = 32;               // per warp: alpha[12], 1/sum[12], pad
+constexpr int kChunk = 8;                     // keys per chunk = K of one tcgen05.mma.kind::tf32
+constexpr int kMaxRows = 20;                  // query rows per CTA
+constexpr int kHalfRows = kMaxRows / 2;       // a logit thread owns rows rp and rp + 10; a value thread rows 10 rg .. 10 rg + 9
+constexpr int kBiasRow = ABX_IPA_BIAS_ROW;    // floats per (chunk, row) of the chunked pair bias (96 used)
+constexpr int kPD = 2;                        // chunks of probabilities in flight
+constexpr int kPTileBytes = 1040;             // per item: hi tile 512 B | lo tile 512 B | 16 B stagger (bank spread)
+constexpr int kPfRow = 24;                    // plain probabilities pf[key][head][24]: row r at r + 2 (r / 10)
+constexpr int kASlots = 12, kACol0 = kMaxRows * 16;   // tensor memory: D_i at columns 16 i, A ring at 320 + 16 slot
+constexpr uint32_t kTmemCols = 512;
+constexpr int kZSlotBytes = kChunk * kCz * 4; // 4096
+constexpr int kKVChunkBytes = kChunk * kKVRow * 4;    // 26112
+constexpr int kThreads = 896;
+constexpr int kRegsCtl = 40, kRegsConv = 48, kRegsSvc = 56, kRegsLogit = 128, kRegsVal = 96;
+static_assert(128 * kRegsCtl + 256 * kRegsConv + 128 * kRegsSvc + 128 * kRegsLogit + 256 * kRegsVal <= 65536, "register budget");
 constexpr int kFeatPt = kH * kSv, kFeatNorm = kFeatPt + 3 * kH * kPv, kFeatPair = kFeatNorm + kH * kPv;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleGap = 64.f;           // log2 units: the reference point moves when a logit exceeds it by this much
 
-__host__ __device__ inline size_t fused_smem_floats(int R) {
-  return (size_t)2 * kChunk * kKVStride + (size_t)R * (kZSlots * kZSlotFloats + kChunk * kH + kQRow + kStatFloats);
+enum Warps { kWarpZ = 0, kWarpMma = 1, kWarpKV = 2, kWarpConv0 = 4, kWarpSvc = 12, kWarpLogit = 16, kWarpVal = 20 };
+
+// ---- shared-memory carve-up (byte offsets from a 128-byte aligned base) ----
+struct Smem {
+  uint32_t kv, bias, ptile, pf, al, linv, mask, ov, zring, bars, total;
+};
+__host__ __device__ inline Smem smem_layout(int N, int zslots) {
+  Smem s;
+  uint32_t o = 0;
+  auto take = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 127u) & ~127u; return r; };
+  s.kv = take(2 * kKVChunkBytes);
+  s.bias = take(2 * kMaxRows * kBiasRow * 4);
+  s.ptile = take(kPD * kMaxRows * kPTileBytes);
+  s.pf = take(kPD * kChunk * kH * kPfRow * 4);
+  s.al = take(kPD * kH * kPfRow * 4);
+  s.linv = take(kH * kPfRow * 4);
+  s.mask = take((uint32_t)((N + kChunk - 1) / kChunk) * kChunk * 4);
+  s.ov = s.kv;                                   // epilogue staging of the value outputs reuses the key/value chunks
+  s.zring = take((uint32_t)zslots * kZSlotBytes);
+  s.bars = take(1024);
+  s.total = o + 128;                             // alignment slack
+  return s;
 }
-__host__ inline size_t fused_smem_bytes(int R) { return fused_smem_floats(R) * sizeof(float) + (4 + (size_t)R * kZSlots) * sizeof(uint64_t); }
+static_assert(kMaxRows * kH * kVD * 4 <= 2 * kKVChunkBytes, "value staging must fit the key/value buffers");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -75,14 +109,64 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 // global -> shared bulk copy (bytes and both addresses multiples of 16) completing on an mbarrier
-__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gmem_src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// orders this thread's earlier generic-proxy shared-memory accesses before later async-proxy (bulk copy) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// B operand tile [16 heads x 8 keys] tf32, K-major without swizzle: core matrices of 8 rows x 16 bytes (128 B, rows 16 B
+// apart); the two k-halves 128 B apart (LBO), the two 8-row groups 256 B apart (SBO).  Descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_ptile(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ uint32_t ptile_offset(int h, int k) {   // byte offset of p[h][k] inside a tile
+  return (uint32_t)((h >> 3) * 256 + (k >> 2) * 128 + (h & 7) * 16 + (k & 3) * 4);
+}
+// instruction descriptor, kind::tf32: D f32, A/B tf32, both K-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ int pf_row(int r) { return r + 2 * (r / kHalfRows); }
 
 }  // namespace
 
@@ -145,276 +229,474 @@ __global__ void __launch_bounds__(256) ipa_pack_nodes_kernel(int B, int N, const
 // ---------------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxRows * 32, 1)
-ipa_fused_kernel(int N, int R, int tiles_per_b, const float* __restrict__ Qp, const float* __restrict__ KVp,
+__global__ void __launch_bounds__(kThreads, 1)
+ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restrict__ Qp, const float* __restrict__ KVp,
                  const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
                  const float* __restrict__ trans, const float* __restrict__ point_weights, const float* __restrict__ z,
                  float* __restrict__ feats) {
-  extern __shared__ __align__(128) float sm[];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const Smem L = smem_layout(N, zslots);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x / tiles_per_b, i0 = (blockIdx.x % tiles_per_b) * R;
-  const int nvalid = min(R, N - i0);                // rows (warps) of this tile that exist
-  float* KV = sm;                                               // [2][8][820]
-  float* ZR = KV + 2 * kChunk * kKVStride + (size_t)warp * kZSlots * kZSlotFloats;   // this warp's z ring [3][512]
-  float* PS = sm + 2 * kChunk * kKVStride + (size_t)R * kZSlots * kZSlotFloats + (size_t)warp * kChunk * kH;   // [8][12]
-  float* QS = sm + 2 * kChunk * kKVStride + (size_t)R * (kZSlots * kZSlotFloats + kChunk * kH) + (size_t)warp * kQRow;
-  float* ST = sm + 2 * kChunk * kKVStride + (size_t)R * (kZSlots * kZSlotFloats + kChunk * kH + kQRow) + (size_t)warp * kStatFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + fused_smem_floats(R));
-  uint64_t* kvfull = bars;                          // [2] bulk copies of a key/value chunk have landed
-  uint64_t* kvempty = bars + 2;                     // [2] every row warp is done with the chunk
-  uint64_t* zfull = bars + 4 + warp * kZSlots;      // [3] this warp's z slots
+  const int nvalid = min(R, N - i0);                // query rows of this tile
+  const int nchunks = (N + kChunk - 1) / kChunk;
+  const int nitems = nchunks * nvalid;              // item k = chunk * nvalid + row
+
+  float* KVs = reinterpret_cast<float*>(sm + L.kv);           // [2][8][816]
+  float* BSs = reinterpret_cast<float*>(sm + L.bias);         // [2][R][100]
+  uint8_t* PT = sm + L.ptile;                                  // [kPD][R] tiles of kPTileBytes
+  float* PF = reinterpret_cast<float*>(sm + L.pf);            // [kPD][8][12][24]
+  float* AL = reinterpret_cast<float*>(sm + L.al);            // [kPD][12][24] rescale factors of the chunk
+  float* LINV = reinterpret_cast<float*>(sm + L.linv);        // [12][24] 1 / row sum
+  float* MS = reinterpret_cast<float*>(sm + L.mask);          // [nchunks * 8] key mask (0 beyond N)
+  uint8_t* ZR = sm + L.zring;                                  // [zslots][4096]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint64_t* kv_full = bars;                         // [2]
+  uint64_t* kv_empty = bars + 2;                    // [2]  4 logit warps + 8 value warps
+  uint64_t* p_full = bars + 4;                      // [kPD] 4 logit warps
+  uint64_t* p_empty = bars + 6;                     // [kPD] MMA commit + 8 value warps
+  uint64_t* a_full = bars + 8;                      // [12] 4 converter warps
+  uint64_t* a_empty = bars + 20;                    // [12] MMA commit
+  uint64_t* req = bars + 32;                        // MMA -> accumulator service
+  uint64_t* resp = bars + 33;                       // 4 service warps -> MMA
+  uint64_t* drain = bars + 34;                      // MMA commit: everything issued so far has completed
+  uint64_t* lsum_ready = bars + 35;                 // 4 logit warps: LINV is final
+  uint64_t* z_full = bars + 40;                     // [zslots]
+  uint64_t* z_empty = z_full + zslots;              // [zslots] 4 converter warps
+  volatile int* req_info = reinterpret_cast<volatile int*>(z_empty + zslots);    // {row or -1, probability buffer}
+  unsigned* resc = reinterpret_cast<unsigned*>(const_cast<int*>(req_info) + 2);  // [4] rows whose reference point moved in chunk c & 3
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resc + 4);
 
   if (threadIdx.x == 0) {
-    mbar_init(kvfull, 1); mbar_init(kvfull + 1, 1);
-    mbar_init(kvempty, nvalid); mbar_init(kvempty + 1, nvalid);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 12); }
+    for (int s = 0; s < kPD; ++s) { mbar_init(p_full + s, 4); mbar_init(p_empty + s, 9); }
+    for (int s = 0; s < kASlots; ++s) { mbar_init(a_full + s, 4); mbar_init(a_empty + s, 1); }
+    mbar_init(req, 1); mbar_init(resp, 4); mbar_init(drain, 1); mbar_init(lsum_ready, 4);
+    for (int s = 0; s < zslots; ++s) { mbar_init(z_full + s, 1); mbar_init(z_empty + s, 4); }
+    for (int s = 0; s < 4; ++s) resc[s] = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (lane == 0) { mbar_init(zfull, 1); mbar_init(zfull + 1, 1); mbar_init(zfull + 2, 1); }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // probability tiles (rows 12-15 of every B tile stay zero), plain probabilities (rows that do not exist stay zero),
+  // rescale factors (1), key mask
+  for (int k = threadIdx.x; k < kPD * kMaxRows * kPTileBytes / 16; k += kThreads) reinterpret_cast<float4*>(PT)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = threadIdx.x; k < kPD * kChunk * kH * kPfRow; k += kThreads) PF[k] = 0.f;
+  for (int k = threadIdx.x; k < kPD * kH * kPfRow; k += kThreads) AL[k] = 1.f;
+  for (int k = threadIdx.x; k < kH * kPfRow; k += kThreads) LINV[k] = 0.f;
+  for (int k = threadIdx.x; k < nchunks * kChunk; k += kThreads) MS[k] = (k < N) ? __ldg(mask + (size_t)b * N + k) : 0.f;
+  fence_proxy_async();
+  tc_fence_before();
   __syncthreads();
-  if (warp >= nvalid) return;                       // no CTA-wide barrier below this line
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
-  const int i = i0 + warp;
-  const size_t bn = (size_t)b * N + i;
-  const int nchunks = (N + kChunk - 1) / kChunk, nq = (N + kZKeys - 1) / kZKeys;
-  const float* zrow = z + bn * (size_t)N * kCz;
-  auto issue_z = [&](int q) {                       // lane 0 only: keys 4q .. 4q+3 of this row into slot q % 3
-    const int slot = q % kZSlots;
-    const uint32_t bytes = (uint32_t)min(kZKeys, N - q * kZKeys) * kCz * sizeof(float);
-    mbar_expect_tx(zfull + slot, bytes);
-    bulk_g2s(ZR + slot * kZSlotFloats, zrow + (size_t)q * kZSlotFloats, bytes, zfull + slot);
-  };
-  // z is an input of the whole layer (not produced by the preceding kernels of the chain): start streaming now
-  if (lane == 0)
-    for (int q = 0; q < kZSlots && q < nq; ++q) issue_z(q);
-
-  griddep_wait();                                   // Qp / KVp come from the kernels launched just before
-  griddep_launch_dependents();
-
-  auto issue_kv = [&](int c) {                      // warp 0, all lanes: chunk c -> buffer c & 1
-    const int buf = c & 1, nk = min(kChunk, N - c * kChunk);
-    if (lane == 0) mbar_expect_tx(kvfull + buf, (uint32_t)nk * kKVRow * sizeof(float));
-    __syncwarp();
-    if (lane < nk)
-      bulk_g2s(KV + (size_t)(buf * kChunk + lane) * kKVStride, KVp + ((size_t)b * N + c * kChunk + lane) * kKVRow,
-               kKVRow * sizeof(float), kvfull + buf);
-  };
-  if (warp == 0) {
-    issue_kv(0);
-    if (nchunks > 1) issue_kv(1);
-  }
-  // this row's packed queries -> shared memory (read as warp-wide broadcasts below)
-  {
-    const float4* src = reinterpret_cast<const float4*>(Qp + bn * kQRow);
-    for (int k = lane; k < kQRow / 4; k += 32) reinterpret_cast<float4*>(QS)[k] = __ldg(src + k);
-  }
-  __syncwarp();
-
-  // lane roles. logits: (key kk = lane & 7, heads 3 hq .. 3 hq + 2); values: float4 slices lane + 32 u of the 480-wide
-  // value row (120 slices: lanes 24-31 hold three); pair row: channels 4 lane .. 4 lane + 3
-  const int kk = lane & 7, hq = lane >> 3;
-  float coef[3];
-#pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    const float pw = __ldg(point_weights + 3 * hq + t);
-    const float gamma = (pw > 20.f) ? pw : log1pf(expf(pw));                       // F.softplus  folding.py:96
-    coef[t] = -0.5f * sqrtf(1.0f / (3.0f * kPqk * 9.0f / 2.0f)) * gamma;           // -1/2 w_point gamma  :97-99
-  }
-  const float mi = __ldg(mask + (size_t)b * N + i);
-  const float* mrow = mask + (size_t)b * N;
-  const float* brow = bias + (((size_t)b * kH + 3 * hq) * N + i) * N;             // head 3 hq + t at brow + t N N
-  const size_t bstride = (size_t)N * N;
-  int hd[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) hd[u] = min((lane + 32 * u) / (kVD / 4), kH - 1);
-  const bool has3 = lane + 96 < kH * kVD / 4;
-
-  float m[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, lsum[3] = {0.f, 0.f, 0.f};
-  float4 oval[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) oval[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 acc[kH][2];
-#pragma unroll
-  for (int h = 0; h < kH; ++h) acc[h][0] = acc[h][1] = make_float2(0.f, 0.f);
-
-  float bnext[3], mnext;
-  {
-    const bool v0 = kk < N;
-#pragma unroll
-    for (int t = 0; t < 3; ++t) bnext[t] = v0 ? __ldg(brow + t * bstride + kk) : 0.f;
-    mnext = v0 ? __ldg(mrow + kk) : 0.f;
-  }
-
-  for (int c = 0; c < nchunks; ++c) {
-    const int j0 = c * kChunk, nk = min(kChunk, N - j0), buf = c & 1;
-    const float* kvp = KV + (size_t)buf * kChunk * kKVStride;
-    const bool valid = j0 + kk < N;
-    float bcur[3] = {bnext[0], bnext[1], bnext[2]};
-    const float mj = mnext;
-    {                                               // bias / mask of the next chunk: in flight during this one
-      const int jn = j0 + kChunk + kk;
-      const bool vn = jn < N;
-#pragma unroll
-      for (int t = 0; t < 3; ++t) bnext[t] = vn ? __ldg(brow + t * bstride + jn) : 0.f;
-      mnext = vn ? __ldg(mrow + jn) : 0.f;
-    }
-    mbar_wait(kvfull + buf, (c >> 1) & 1);
-
-    // ---- logits of (key kk, heads 3 hq + t), in units of log 2 ----
-    float s[3];
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const float4* kp = reinterpret_cast<const float4*>(kvp + kk * kKVStride + (3 * hq + t) * kQK);
-      const float4* qp = reinterpret_cast<const float4*>(QS + (3 * hq + t) * kQK);
-      float2 dot = make_float2(0.f, 0.f), dd = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < kSqk / 4; ++u) {
-        const float4 kv = kp[u], qv = qp[u];
-        dot = ffma2(make_float2(qv.x, qv.y), make_float2(kv.x, kv.y), dot);
-        dot = ffma2(make_float2(qv.z, qv.w), make_float2(kv.z, kv.w), dot);
-      }
-#pragma unroll
-      for (int u = kSqk / 4; u < kQK / 4; ++u) {
-        const float4 kv = kp[u], qv = qp[u];
-        const float2 d0 = make_float2(qv.x - kv.x, qv.y - kv.y), d1 = make_float2(qv.z - kv.z, qv.w - kv.w);
-        dd = ffma2(d0, d0, dd);
-        dd = ffma2(d1, d1, dd);
-      }
-      const float lg = (((dot.x + dot.y) + coef[t] * (dd.x + dd.y)) + bcur[t]) * kLog2e;
-      s[t] = valid ? ((mi * mj != 0.f) ? lg : -FLT_MAX) : -INFINITY;               // mask_2d  folding.py:106-109
-    }
-    // ---- online softmax: running max per head over the 8 lanes that share hq ----
-    float alpha[3];
-    bool moved = false;
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      float cm = s[t];
-      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
-      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 4));
-      const float mn = fmaxf(m[t], cm);
-      alpha[t] = exp2f(m[t] - mn);
-      moved |= (mn != m[t]);
-      m[t] = mn;
-      const float p = exp2f(s[t] - mn);
-      lsum[t] = fmaf(lsum[t], alpha[t], p);
-      PS[kk * kH + 3 * hq + t] = p;
-      if (kk == 0) ST[3 * hq + t] = alpha[t];
-    }
-    const bool rescale = __any_sync(0xffffffffu, moved);
-    __syncwarp();
-
-    // ---- values: oval += p[key, head] * V[key, head, :] ----
-    if (rescale) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float a = ST[hd[u]];
-        oval[u].x *= a; oval[u].y *= a; oval[u].z *= a; oval[u].w *= a;
-      }
-    }
-    for (int k8 = 0; k8 < nk; ++k8) {
-      const float4* vp = reinterpret_cast<const float4*>(kvp + k8 * kKVStride + kVOff) + lane;
-      const float* pr = PS + k8 * kH;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (u < 3 || has3) {
-          const float4 v = vp[32 * u];
-          const float p = pr[hd[u]];
-          oval[u].x = fmaf(p, v.x, oval[u].x); oval[u].y = fmaf(p, v.y, oval[u].y);
-          oval[u].z = fmaf(p, v.z, oval[u].z); oval[u].w = fmaf(p, v.w, oval[u].w);
+  const int wg = warp >> 2;
+  if (wg == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
+    if (warp == kWarpZ && lane == 0) {
+      // ---------------- z producer (z is an input of the whole layer: it does not wait for the preceding kernels) ----------------
+      const uint8_t* zb = reinterpret_cast<const uint8_t*>(z + ((size_t)b * N + i0) * (size_t)N * kCz);
+      const size_t row_bytes = (size_t)N * kCz * 4;
+      int slot = 0;
+      uint32_t ph = 1;                               // parity of the "empty" phase that precedes the slot's next use
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t bytes = (uint32_t)min(kChunk, N - c * kChunk) * kCz * 4;
+        for (int r = 0; r < nvalid; ++r) {
+          mbar_wait(z_empty + slot, ph);
+          mbar_expect_tx(z_full + slot, bytes);
+          bulk_g2s(ZR + (size_t)slot * kZSlotBytes, zb + (size_t)r * row_bytes + (size_t)c * kZSlotBytes, bytes, z_full + slot);
+          if (++slot == zslots) { slot = 0; ph ^= 1; }
         }
       }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(kvempty + buf);       // this row is done with the chunk's keys / values
-    if (warp == 0 && c + 2 < nchunks) {              // refill the buffer once every row has released it
-      mbar_wait(kvempty + buf, (c >> 1) & 1);
-      fence_proxy_async();
-      issue_kv(c + 2);
-    }
-
-    // ---- pair row: acc[h] += p[key, h] * z[i, key, :] ----
-    if (rescale) {
-#pragma unroll
-      for (int h = 0; h < kH; ++h) {
-        const float a = ST[h];
-        acc[h][0].x *= a; acc[h][0].y *= a; acc[h][1].x *= a; acc[h][1].y *= a;
+    } else if (warp == kWarpKV && lane == 0) {
+      // ---------------- key/value + pair-bias producer ----------------
+      griddep_wait();                                // Qp / KVp come from the kernels launched just before
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1, nk = min(kChunk, N - c * kChunk);
+        mbar_wait(kv_empty + buf, ((c >> 1) & 1) ^ 1);
+        const uint32_t kvb = (uint32_t)nk * kKVRow * 4, bb = (uint32_t)nvalid * kBiasRow * 4;
+        mbar_expect_tx(kv_full + buf, kvb + bb);
+        bulk_g2s(KVs + (size_t)buf * kChunk * kKVRow, KVp + ((size_t)b * N + c * kChunk) * kKVRow, kvb, kv_full + buf);
+        bulk_g2s(BSs + (size_t)buf * kMaxRows * kBiasRow, bias + (((size_t)b * nchunks + c) * N + i0) * kBiasRow, bb, kv_full + buf);
       }
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int q = 2 * c + half;
-      if (q < nq) {
-        const int slot = q % kZSlots, nz = min(kZKeys, N - q * kZKeys);
-        mbar_wait(zfull + slot, (q / kZSlots) & 1);
-        const float4* zs = reinterpret_cast<const float4*>(ZR + slot * kZSlotFloats) + lane;
-        for (int k4 = 0; k4 < nz; ++k4) {
-          const float4 zv = zs[k4 * (kCz / 4)];
-          const float4* ap = reinterpret_cast<const float4*>(PS + (half * kZKeys + k4) * kH);
-          float a[kH];
-#pragma unroll
-          for (int u = 0; u < kH / 4; ++u) { const float4 v = ap[u]; a[4 * u] = v.x; a[4 * u + 1] = v.y; a[4 * u + 2] = v.z; a[4 * u + 3] = v.w; }
-          const float2 zlo = make_float2(zv.x, zv.y), zhi = make_float2(zv.z, zv.w);
-#pragma unroll
-          for (int h = 0; h < kH; ++h) {
-            const float2 aa = make_float2(a[h], a[h]);
-            acc[h][0] = ffma2(aa, zlo, acc[h][0]);
-            acc[h][1] = ffma2(aa, zhi, acc[h][1]);
+    } else if (warp == kWarpMma) {
+      // ---------------- MMA issuer ----------------
+      if (lane == 0) {
+        uint32_t dr = 0, rs = 0;
+        int k = 0, aslot = 0;
+        uint32_t aph = 0;
+        for (int c = 0; c < nchunks; ++c) {
+          const int pb = c % kPD;
+          mbar_wait(p_full + pb, (c / kPD) & 1);
+          tc_fence_after();
+          const unsigned rm = *reinterpret_cast<volatile unsigned*>(resc + (c & 3));
+          for (int r = 0; r < nvalid; ++r, ++k) {
+            mbar_wait(a_full + aslot, aph);
+            tc_fence_after();
+            if ((rm >> r) & 1u) {                    // the reference point of some head of row r moved: rescale D_r first
+              umma_commit(drain);
+              mbar_wait(drain, dr); dr ^= 1;
+              req_info[0] = r; req_info[1] = pb;
+              mbar_arrive(req);
+              mbar_wait(resp, rs); rs ^= 1;
+              tc_fence_after();
+            }
+            const uint32_t d = tmem_base + 16u * r;
+            const uint32_t a_hi = tmem_base + kACol0 + 16u * aslot, a_lo = a_hi + 8u;
+            const uint64_t b_hi = umma_desc_ptile(smem_u32(PT + (size_t)(pb * kMaxRows + r) * kPTileBytes));
+            const uint64_t b_lo = b_hi + (512 >> 4);
+            umma_tf32_ts(d, a_hi, b_lo, c > 0 ? 1u : 0u);
+            umma_tf32_ts(d, a_lo, b_hi, 1u);
+            umma_tf32_ts(d, a_hi, b_hi, 1u);
+            umma_commit(a_empty + aslot);            // A slot free once these MMAs have read it
+            if (++aslot == kASlots) { aslot = 0; aph ^= 1; }
           }
+          umma_commit(p_empty + pb);                 // probability tiles of the chunk consumed
         }
-        __syncwarp();                                // every lane has read the slot
-        if (lane == 0 && q + kZSlots < nq) { fence_proxy_async(); issue_z(q + kZSlots); }
+        umma_commit(drain);
+        mbar_wait(drain, dr);
+        req_info[0] = -1; req_info[1] = 0;
+        mbar_arrive(req);
       }
     }
-    __syncwarp();                                    // PS / ST are rewritten by the next chunk
-  }
-
-  // ---- normalise and write the 2112-wide feature row of residue i ----
+  } else if (wg == 1 || wg == 2) {
+    // ---------------- converters: z item (8 keys x 128 channels in shared memory) -> A hi / lo in tensor memory ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConv));
+    const int cw = wg - 1;                           // this warpgroup converts items cw, cw + 2, ...
+    const int q = warp & 3, ch = 32 * q + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + kACol0;
+    int pend = -1;                                   // A slot whose stores are in flight
+    int c = 0, r = cw;
+    while (r >= nvalid && c < nchunks) { r -= nvalid; ++c; }
+    for (int k = cw; k < nitems; k += 2) {
+      const int zs = k % zslots, as = k % kASlots;
+      const int nk = min(kChunk, N - c * kChunk);
+      mbar_wait(z_full + zs, (uint32_t)(k / zslots) & 1u);
+      const float* zp = reinterpret_cast<const float*>(ZR + (size_t)zs * kZSlotBytes) + ch;
+      uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    float l = lsum[t];
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    l += __shfl_xor_sync(0xffffffffu, l, 4);
-    if (kk == 0) ST[16 + 3 * hq + t] = 1.f / l;
-  }
-  __syncwarp();
-  float* frow = feats + bn * kFeat;
+      for (int kk = 0; kk < kChunk; ++kk) hi[kk] = (kk < nk) ? __float_as_uint(zp[kk * kCz]) : 0u;
+      if (pend >= 0) {                               // previous item: stores done -> hand the slot to the MMA issuer
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + pend);
+      }
 #pragma unroll
-  for (int h = 0; h < kH; ++h) {                     // 'b i h c -> b i (h c)'  folding.py:126-127
-    const float inv = ST[16 + h];
-    *reinterpret_cast<float4*>(frow + kFeatPair + h * kCz + 4 * lane) =
-        make_float4(acc[h][0].x * inv, acc[h][0].y * inv, acc[h][1].x * inv, acc[h][1].y * inv);
-  }
-  float* OV = ZR;                                    // the z ring is idle now: stage the 480 value outputs
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (u < 3 || has3) {
-      const float inv = ST[16 + hd[u]];
-      reinterpret_cast<float4*>(OV)[lane + 32 * u] = make_float4(oval[u].x * inv, oval[u].y * inv, oval[u].z * inv, oval[u].w * inv);
+      for (int kk = 0; kk < kChunk; ++kk)
+        lo[kk] = __float_as_uint(__uint_as_float(hi[kk]) - __uint_as_float(hi[kk] & 0xffffe000u));
+      __syncwarp();                                  // every lane has read the z slot
+      if (lane == 0) mbar_arrive(z_empty + zs);
+      mbar_wait(a_empty + as, ((uint32_t)(k / kASlots) & 1u) ^ 1u);
+      tc_fence_after();
+      tmem_st8(lane_base + 16u * as, hi);
+      tmem_st8(lane_base + 16u * as + 8u, lo);
+      pend = as;
+      r += 2;
+      while (r >= nvalid) { r -= nvalid; ++c; }
     }
-  }
-  __syncwarp();
-  for (int e = lane; e < kH * kSv; e += 32) frow[e] = OV[(e / kSv) * kVD + (e % kSv)];       // 'b i h c -> b i (h c)'  :115
-  {
-    float Rm[9], tr[3], it[3];
+    if (pend >= 0) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + pend);
+    }
+  } else if (wg == 3) {
+    // ---------------- accumulator service: rescale D_r on request; final normalisation + o_pair store ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsSvc));
+    const int q = warp & 3, ch = 32 * q + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
+    uint32_t ph = 0;
+    for (;;) {
+      mbar_wait(req, ph); ph ^= 1;
+      const int r = req_info[0], pb = req_info[1];
+      if (r < 0) break;
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld16(lane_base + 16u * r, v);
+      const float* al = AL + (size_t)pb * kH * kPfRow + pf_row(r);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Rm[k] = __ldg(rots + bn * 9 + k);
+      for (int h = 0; h < kH; ++h) v[h] = __float_as_uint(__uint_as_float(v[h]) * al[h * kPfRow]);
+      tmem_st16(lane_base + 16u * r, v);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(resp);
+    }
+    tc_fence_after();
+    mbar_wait(lsum_ready, 0);
+    for (int r = 0; r < nvalid; ++r) {
+      uint32_t v[16];
+      tmem_ld16(lane_base + 16u * r, v);
+      float* frow = feats + ((size_t)b * N + i0 + r) * kFeat + kFeatPair + ch;       // 'b i h c -> b i (h c)'  folding.py:126-127
+      const float* li = LINV + pf_row(r);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) tr[k] = __ldg(trans + bn * 3 + k);
-    // invert_rigids (r3.py:54-59): R^T, -(R^T t); then rigids_apply  folding.py:121
+      for (int h = 0; h < kH; ++h) frow[h * kCz] = __uint_as_float(v[h]) * li[h * kPfRow];
+    }
+  } else if (wg == 4) {
+    // ---------------- logits + softmax: thread = (head h, query rows rp and rp + 10), all keys of the chunk ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsLogit));
+    griddep_wait();                                  // Qp comes from the kernels launched just before
+    const int t = threadIdx.x - kWarpLogit * 32;
+    const bool worker = t < kH * kHalfRows;
+    const int h = worker ? t / kHalfRows : 0, rp = worker ? t % kHalfRows : 0;
+    const int r0 = rp, r1 = rp + kHalfRows;
+    const bool act0 = worker && r0 < nvalid, act1 = worker && r1 < nvalid;
+    float q0[kQK], q1[kQK];
+    {
+      const float4* s0 = reinterpret_cast<const float4*>(Qp + ((size_t)b * N + i0 + (act0 ? r0 : 0)) * kQRow + h * kQK);
+      const float4* s1 = reinterpret_cast<const float4*>(Qp + ((size_t)b * N + i0 + (act1 ? r1 : 0)) * kQRow + h * kQK);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) it[k] = -(Rm[k] * tr[0] + Rm[3 + k] * tr[1] + Rm[6 + k] * tr[2]);
-    for (int pi = lane; pi < kH * kPv; pi += 32) {
-      const int h = pi / kPv, p = pi % kPv;
-      const float* g = OV + h * kVD + kSv + 3 * p;
-      float l[3];
+      for (int u = 0; u < kQK / 4; ++u) {
+        const float4 a = __ldg(s0 + u), c4 = __ldg(s1 + u);
+        q0[4 * u] = a.x; q0[4 * u + 1] = a.y; q0[4 * u + 2] = a.z; q0[4 * u + 3] = a.w;
+        q1[4 * u] = c4.x; q1[4 * u + 1] = c4.y; q1[4 * u + 2] = c4.z; q1[4 * u + 3] = c4.w;
+      }
+    }
+    const float pw = __ldg(point_weights + h);
+    const float gamma = (pw > 20.f) ? pw : log1pf(expf(pw));                       // F.softplus  folding.py:96
+    const float coef = -0.5f * sqrtf(1.0f / (3.0f * kPqk * 9.0f / 2.0f)) * gamma;  // -1/2 w_point gamma  :97-99
+    const float mi0 = act0 ? __ldg(mask + (size_t)b * N + i0 + r0) : 0.f;
+    const float mi1 = act1 ? __ldg(mask + (size_t)b * N + i0 + r1) : 0.f;
+    float m0 = -FLT_MAX, m1 = -FLT_MAX, l0 = 0.f, l1 = 0.f;
+    const float2 neg1 = make_float2(-1.f, -1.f);
+
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1, pb = c % kPD, j0 = c * kChunk;
+      mbar_wait(kv_full + buf, (c >> 1) & 1);
+      mbar_wait(p_empty + pb, ((c / kPD) & 1) ^ 1);
+      if (t == 0) resc[(c + 2) & 3] = 0u;
+      const float* kvp = KVs + (size_t)buf * kChunk * kKVRow + h * kQK;
+      const float* bs0 = BSs + ((size_t)buf * kMaxRows + r0) * kBiasRow + h;
+      const float* bs1 = BSs + ((size_t)buf * kMaxRows + r1) * kBiasRow + h;
+      float s0[kChunk], s1[kChunk];
+#pragma unroll
+      for (int kk = 0; kk < kChunk; ++kk) {
+        const float4* kp = reinterpret_cast<const float4*>(kvp + kk * kKVRow);
+        float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f), e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kSqk / 4; ++u) {
+          const float4 kv = kp[u];
+          const float2 ka = make_float2(kv.x, kv.y), kb = make_float2(kv.z, kv.w);
+          d0 = ffma2(make_float2(q0[4 * u], q0[4 * u + 1]), ka, d0);
+          d0 = ffma2(make_float2(q0[4 * u + 2], q0[4 * u + 3]), kb, d0);
+          d1 = ffma2(make_float2(q1[4 * u], q1[4 * u + 1]), ka, d1);
+          d1 = ffma2(make_float2(q1[4 * u + 2], q1[4 * u + 3]), kb, d1);
+        }
+#pragma unroll
+        for (int u = kSqk / 4; u < kQK / 4; ++u) {
+          const float4 kv = kp[u];
+          const float2 ka = make_float2(kv.x, kv.y), kb = make_float2(kv.z, kv.w);
+          const float2 a0 = ffma2(ka, neg1, make_float2(q0[4 * u], q0[4 * u + 1])), b0 = ffma2(kb, neg1, make_float2(q0[4 * u + 2], q0[4 * u + 3]));
+          const float2 a1 = ffma2(ka, neg1, make_float2(q1[4 * u], q1[4 * u + 1])), b1 = ffma2(kb, neg1, make_float2(q1[4 * u + 2], q1[4 * u + 3]));
+          e0 = ffma2(a0, a0, e0); e0 = ffma2(b0, b0, e0);
+          e1 = ffma2(a1, a1, e1); e1 = ffma2(b1, b1, e1);
+        }
+        const float mj = MS[j0 + kk];
+        const float lg0 = (((d0.x + d0.y) + coef * (e0.x + e0.y)) + bs0[kk * kH]) * kLog2e;   // log-2 units
+        const float lg1 = (((d1.x + d1.y) + coef * (e1.x + e1.y)) + bs1[kk * kH]) * kLog2e;
+        s0[kk] = (mi0 * mj != 0.f) ? lg0 : -FLT_MAX;                                           // mask_2d  folding.py:106-109
+        s1[kk] = (mi1 * mj != 0.f) ? lg1 : -FLT_MAX;
+      }
+      const int nk = min(kChunk, N - j0);
+      auto softmax_row = [&](float (&s)[kChunk], float& m, float& l, int r, bool act) {
+        if (!act) return;
+        float cm = -FLT_MAX;
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) cm = (kk < nk) ? fmaxf(cm, s[kk]) : cm;
+        float alpha = 1.f;
+        if (c == 0) {
+          m = cm;
+        } else if (cm > m + kRescaleGap) {           // move the reference point: accumulators are scaled by alpha
+          alpha = exp2f(m - cm);
+          m = cm;
+          l *= alpha;
+          atomicOr(resc + (c & 3), 1u << r);
+        }
+        AL[((size_t)pb * kH + h) * kPfRow + pf_row(r)] = alpha;
+        float p[kChunk];
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) {
+          p[kk] = (kk < nk) ? exp2f(s[kk] - m) : 0.f;
+          l += p[kk];
+        }
+        uint8_t* tile = PT + (size_t)(pb * kMaxRows + r) * kPTileBytes;
+        float ph[kChunk], pl[kChunk];
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) {
+          ph[kk] = __uint_as_float(__float_as_uint(p[kk]) & 0xffffe000u);
+          pl[kk] = p[kk] - ph[kk];
+        }
+        *reinterpret_cast<float4*>(tile + ptile_offset(h, 0)) = make_float4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<float4*>(tile + ptile_offset(h, 4)) = make_float4(ph[4], ph[5], ph[6], ph[7]);
+        *reinterpret_cast<float4*>(tile + 512 + ptile_offset(h, 0)) = make_float4(pl[0], pl[1], pl[2], pl[3]);
+        *reinterpret_cast<float4*>(tile + 512 + ptile_offset(h, 4)) = make_float4(pl[4], pl[5], pl[6], pl[7]);
+        float* pf = PF + ((size_t)pb * kChunk * kH + h) * kPfRow + pf_row(r);
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) pf[kk * kH * kPfRow] = p[kk];
+      };
+      softmax_row(s0, m0, l0, r0, act0);
+      softmax_row(s1, m1, l1, r1, act1);
+      fence_proxy_async();                           // the probability tiles are read by the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(p_full + pb); mbar_arrive(kv_empty + buf); }
+    }
+    if (act0) LINV[h * kPfRow + pf_row(r0)] = 1.f / l0;
+    if (act1) LINV[h * kPfRow + pf_row(r1)] = 1.f / l1;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(lsum_ready);
+  } else {
+    // ---------------- attention over the value rows: thread = (row group rg: rows 10 rg .. 10 rg + 9, head h, dims 4 d4 ..) ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsVal));
+    const int t = threadIdx.x - kWarpVal * 32;
+    const bool worker = t < 2 * kH * (kVD / 4);
+    const int rg = worker ? t / (kH * (kVD / 4)) : 0, dg = worker ? t % (kH * (kVD / 4)) : 0;
+    const int h = dg / (kVD / 4), d4 = dg % (kVD / 4);
+    float2 acc[kHalfRows / 2][4];                    // [row pair][dim]: (row 2j, row 2j + 1)
+#pragma unroll
+    for (int j = 0; j < kHalfRows / 2; ++j)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) acc[j][d] = make_float2(0.f, 0.f);
+
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1, pb = c % kPD, nk = min(kChunk, N - c * kChunk);
+      mbar_wait(kv_full + buf, (c >> 1) & 1);
+      mbar_wait(p_full + pb, (c / kPD) & 1);
+      {
+        const float4* ap = reinterpret_cast<const float4*>(AL + ((size_t)pb * kH + h) * kPfRow + rg * 12);
+        const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
+        const bool moved = (a0.x != 1.f) | (a0.y != 1.f) | (a0.z != 1.f) | (a0.w != 1.f) | (a1.x != 1.f) | (a1.y != 1.f) |
+                           (a1.z != 1.f) | (a1.w != 1.f) | (a2.x != 1.f) | (a2.y != 1.f);
+        if (moved) {
+          const float2 f[5] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w),
+                               make_float2(a2.x, a2.y)};
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) { acc[j][d].x *= f[j].x; acc[j][d].y *= f[j].y; }
+        }
+      }
+      const float* vbase = KVs + (size_t)buf * kChunk * kKVRow + kVOff + h * kVD + 4 * d4;
+      const float* pbase = PF + ((size_t)pb * kChunk * kH + h) * kPfRow + rg * 12;
+      for (int kk = 0; kk < nk; ++kk) {
+        const float4 v = *reinterpret_cast<const float4*>(vbase + kk * kKVRow);
+        const float4* pp = reinterpret_cast<const float4*>(pbase + kk * kH * kPfRow);
+        const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
+        const float2 pr[5] = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w), make_float2(p1.x, p1.y), make_float2(p1.z, p1.w),
+                              make_float2(p2.x, p2.y)};
+        const float2 vx = make_float2(v.x, v.x), vy = make_float2(v.y, v.y), vz = make_float2(v.z, v.z), vw = make_float2(v.w, v.w);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          acc[j][0] = ffma2(pr[j], vx, acc[j][0]);
+          acc[j][1] = ffma2(pr[j], vy, acc[j][1]);
+          acc[j][2] = ffma2(pr[j], vz, acc[j][2]);
+          acc[j][3] = ffma2(pr[j], vw, acc[j][3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(p_empty + pb); mbar_arrive(kv_empty + buf); }
+    }
+
+    // ---- normalise, stage the 480 value outputs of every row, then write o_scalar / o_point / o_point_norm ----
+    mbar_wait(lsum_ready, 0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // every value warp is done with the key/value buffers
+    float* OV = reinterpret_cast<float*>(sm + L.ov); // [R][480]
+    if (worker) {
+      const float4* lp = reinterpret_cast<const float4*>(LINV + h * kPfRow + rg * 12);
+      const float4 i0v = lp[0], i1v = lp[1], i2v = lp[2];
+      const float inv[10] = {i0v.x, i0v.y, i0v.z, i0v.w, i1v.x, i1v.y, i1v.z, i1v.w, i2v.x, i2v.y};
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int ra = rg * kHalfRows + 2 * j;
+        *reinterpret_cast<float4*>(OV + (size_t)ra * (kH * kVD) + h * kVD + 4 * d4) =
+            make_float4(acc[j][0].x * inv[2 * j], acc[j][1].x * inv[2 * j], acc[j][2].x * inv[2 * j], acc[j][3].x * inv[2 * j]);
+        *reinterpret_cast<float4*>(OV + (size_t)(ra + 1) * (kH * kVD) + h * kVD + 4 * d4) =
+            make_float4(acc[j][0].y * inv[2 * j + 1], acc[j][1].y * inv[2 * j + 1], acc[j][2].y * inv[2 * j + 1], acc[j][3].y * inv[2 * j + 1]);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int e = t; e < nvalid * kH * kSv; e += 256) {                                          // 'b i h c -> b i (h c)'  :115
+      const int r = e / (kH * kSv), o = e % (kH * kSv);
+      feats[((size_t)b * N + i0 + r) * kFeat + o] = OV[(size_t)r * (kH * kVD) + (o / kSv) * kVD + (o % kSv)];
+    }
+    for (int e = t; e < nvalid * kH * kPv; e += 256) {
+      const int r = e / (kH * kPv), pi = e % (kH * kPv), hh = pi / kPv, p = pi % kPv;
+      const size_t bn = (size_t)b * N + i0 + r;
+      float Rm[9], tr[3], it[3], l[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Rm[k] = __ldg(rots + bn * 9 + k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) tr[k] = __ldg(trans + bn * 3 + k);
+      // invert_rigids (r3.py:54-59): R^T, -(R^T t); then rigids_apply  folding.py:121
+#pragma unroll
+      for (int k = 0; k < 3; ++k) it[k] = -(Rm[k] * tr[0] + Rm[3 + k] * tr[1] + Rm[6 + k] * tr[2]);
+      const float* g = OV + (size_t)r * (kH * kVD) + hh * kVD + kSv + 3 * p;
 #pragma unroll
       for (int k = 0; k < 3; ++k) l[k] = it[k] + (Rm[k] * g[0] + Rm[3 + k] * g[1] + Rm[6 + k] * g[2]);
+      float* frow = feats + bn * kFeat;
 #pragma unroll
       for (int k = 0; k < 3; ++k) frow[kFeatPt + k * (kH * kPv) + pi] = l[k];                  // '(r n)'  folding.py:122
       frow[kFeatNorm + pi] = sqrtf(l[0] * l[0] + l[1] * l[1] + l[2] * l[2] + 1e-8f);           // :123
     }
   }
+
+  griddep_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// chunked key-major pair bias: out[b][c][i][12 k + h] = sqrt(1/3) (z[b,i,8c+k,:] . w[h,:] + b[h])   folding.py:101-104
+// One CTA per (b, i, 64-key tile): the z tile is staged in shared memory (row stride 132 floats: conflict-free
+// float4 reads with lanes on consecutive keys), thread = (key, group of 3 heads).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBiasJ = 64, kZld = kCz + 4;
+
+__global__ void __launch_bounds__(256) ipa_pair_bias_chunked_kernel(int N, const float* __restrict__ z,
+                                                                    const float* __restrict__ w_pair,
+                                                                    const float* __restrict__ b_pair, float* __restrict__ bias) {
+  __shared__ __align__(16) float zs[kBiasJ * kZld];
+  __shared__ __align__(16) float ws[kH * kCz];
+  const int j0 = blockIdx.x * kBiasJ, i = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int nchunks = (N + kChunk - 1) / kChunk;
+  for (int k = tid; k < kH * kCz / 4; k += 256)
+    reinterpret_cast<float4*>(ws)[k] = __ldg(reinterpret_cast<const float4*>(w_pair) + k);
+  const float4* zrow = reinterpret_cast<const float4*>(z + (((size_t)b * N + i) * N + j0) * kCz);
+  const int nj = min(kBiasJ, N - j0);
+  for (int k = tid; k < nj * (kCz / 4); k += 256) {
+    const int jj = k / (kCz / 4), c4 = k % (kCz / 4);
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(zrow + k));
+    *reinterpret_cast<float4*>(&zs[jj * kZld + 4 * c4]) = v;
+  }
+  __syncthreads();
+  const int jj = tid % kBiasJ, hg = tid / kBiasJ;     // heads 3*hg .. 3*hg+2
+  if (jj >= nj) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 8
+  for (int c = 0; c < kCz; c += 4) {
+    const float4 zv = *reinterpret_cast<const float4*>(&zs[jj * kZld + c]);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[(3 * hg + u) * kCz + c]);
+      acc[u] = fmaf(zv.x, wv.x, acc[u]); acc[u] = fmaf(zv.y, wv.y, acc[u]);
+      acc[u] = fmaf(zv.z, wv.z, acc[u]); acc[u] = fmaf(zv.w, wv.w, acc[u]);
+    }
+  }
+  const float w_pair_scale = sqrtf(1.0f / 3.0f);
+  const int j = j0 + jj;
+  float* dst = bias + (((size_t)b * nchunks + j / kChunk) * N + i) * kBiasRow + (j % kChunk) * kH + 3 * hg;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) dst[u] = w_pair_scale * (acc[u] + __ldg(b_pair + 3 * hg + u));
 }
 
 // Tile height: time ~ rounds * (R + 6.4) — R rows of z per tile plus the tile's key / value chunks (3264 B per key
@@ -442,6 +724,13 @@ static int fused_sm_count() {
 
 size_t ipa_fused_qp_floats(int B, int N) { return (size_t)B * N * kQRow; }
 size_t ipa_fused_kvp_floats(int B, int N) { return (size_t)B * N * kKVRow; }
+size_t ipa_pair_bias_floats(int B, int N) { return (size_t)B * ceil_div(N, kChunk) * N * kBiasRow; }
+
+int launch_ipa_pair_bias(cudaStream_t s, int B, int N, const float* z, const float* w_pair, const float* b_pair, float* bias) {
+  ipa_pair_bias_chunked_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), 256, 0, s>>>(N, z, w_pair, b_pair, bias);
+  count_launch();
+  return check_launch("ipa_pair_bias_chunked_kernel");
+}
 
 int launch_ipa_pack_nodes(cudaStream_t s, int B, int N, const float* proj, const float* rots, const float* trans,
                           float* Qp, float* KVp) {
@@ -456,10 +745,14 @@ int launch_ipa_fused(cudaStream_t s, int B, int N, const float* Qp, const float*
                      const float* rots, const float* trans, const float* point_weights, const float* z, float* feats) {
   const int R = choose_rows(B, N, fused_sm_count());
   const int tiles_per_b = ceil_div(N, R);
-  const size_t smem = fused_smem_bytes(R);
-  ABX_CUDA(cudaFuncSetAttribute(ipa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(kMaxRows)));
-  const cudaError_t le = launch_kernel(ipa_fused_kernel, dim3(B * tiles_per_b), dim3(32 * R), smem, s, N, R, tiles_per_b, Qp, KVp,
-                                       bias, mask, rots, trans, point_weights, z, feats);
+  // z ring: as many 4 KB slots as the 227 KB of shared memory leave (at most 32)
+  int zslots = 32;
+  while (zslots > 4 && smem_layout(N, zslots).total > 227 * 1024) --zslots;
+  const Smem L = smem_layout(N, zslots);
+  ABX_REQUIRE(L.total <= 227 * 1024, "ipa_fused: N=%d needs %u bytes of shared memory", N, L.total);
+  ABX_CUDA(cudaFuncSetAttribute(ipa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const cudaError_t le = launch_kernel(ipa_fused_kernel, dim3(B * tiles_per_b), dim3(kThreads), (size_t)L.total, s, N, R, tiles_per_b,
+                                       zslots, Qp, KVp, bias, mask, rots, trans, point_weights, z, feats);
   count_launch();
   if (le != cudaSuccess) { set_error("launch of ipa_fused_kernel failed: %s", cudaGetErrorString(le)); return ABX_ERR_CUDA; }
   return check_launch("ipa_fused_kernel");

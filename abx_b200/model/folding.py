@@ -68,11 +68,12 @@ class InvariantPointAttention(nn.Module):
         return self._wstruct[1]
 
     def pair_bias(self, inputs_2d):
-        """sqrt(1/3) * proj_pair(z), head-major [B,H,N,N] (folding.py:101-104) — reusable across calls that
-        share `inputs_2d` and weights (the 8 iterations of IpaScore)."""
+        """sqrt(1/3) * proj_pair(z) (folding.py:101-104) in the chunked key-major layout of the fused kernel
+        ([B, ceil(N/8), N, 100], include/abx_b200.h) — reusable across calls that share `inputs_2d` and weights
+        (the 8 iterations of IpaScore)."""
         B, N = inputs_2d.shape[:2]
         z = inputs_2d.float().contiguous()
-        out = torch.empty(B, self.config.num_head, N, N, device=z.device, dtype=torch.float32)
+        out = torch.empty(self._lib.abx_ipa_pair_bias_floats(B, N), device=z.device, dtype=torch.float32)
         with lib.device_guard(z):
             lib.check(self._lib.abx_ipa_pair_bias(lib.stream(), B, N, lib.ptr(z), lib.ptr(self.proj_pair.weight.detach()),
                                                   lib.ptr(self.proj_pair.bias.detach()), lib.ptr(out)))

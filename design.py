@@ -1,10 +1,11 @@
 """Drop-in for the reference's `design.py`: the same driver for ONE complex given as a PDB file named
 `<code>_<heavy>_<light>_<antigen chains>.pdb` (design.py:152,318,349,407).
 
-The reference numbers the antibody chains with ANARCI (IMGT) to find the CDRs; ANARCI is an un-vendored
-dependency that is not available here, so the CDR definition must come with the input: either the PDB is
-already IMGT-numbered (residue numbers 27-38 / 56-65 / 105-117 are CDR1/2/3) or a sidecar
-`<pdb_file>.cdr.json` gives {"H": [[start,end],...3], "L": [[start,end],...3]} as 0-based index ranges.
+The reference numbers the antibody chains with ANARCI (IMGT), keeps the variable domains and labels the CDRs by IMGT
+position.  ANARCI is not available offline: `abx_b200/data/numbering.py` locates the domain and the regions from the
+conserved IMGT anchors (Cys23, Trp41, Cys104, the [WF]G.G J motif) or from the residue numbers when the file is already
+IMGT-numbered, and refuses chains where that fails.  A sidecar `<pdb_file>.cdr.json` = {"H": [[start,end] x 3],
+"L": [[start,end] x 3]} (0-based inclusive index ranges into the chain as read) overrides it.
 """
 import json
 import os
@@ -14,26 +15,25 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from abx_b200 import cli  # noqa: E402
+from abx_b200.data.numbering import NumberingError, assign_regions  # noqa: E402
 
-IMGT_CDRS = ((27, 38), (56, 65), (105, 117))
 
-
-def _cdr_def(chain, first_region, ranges=None):
-    """Region ids 0..6 (heavy) / 7..13 (light): FR1, CDR1, FR2, CDR2, FR3, CDR3, FR4 (residue_constants.py:14)."""
+def _domain(chain, kind, ranges=None):
+    """-> (slice of the chain that is kept, region ids 0..6 (heavy) / 7..13 (light) of the kept residues)."""
     L = len(chain['str_seq'])
-    out = np.zeros(L, np.int64)
-    if ranges is None:
-        num = chain['resseq']
-        if num.max() < 105:
-            raise SystemExit('design.py: the antibody chains are not IMGT-numbered and no .cdr.json sidecar was given '
-                             '(ANARCI is not available offline)')
-        bounds = [int(np.searchsorted(num, v)) for lo, hi in IMGT_CDRS for v in (lo, hi + 1)]
-    else:
+    if ranges is not None:
         bounds = [v for lo, hi in ranges for v in (lo, hi + 1)]
-    edges = [0] + bounds + [L]
-    for r in range(7):
-        out[edges[r]:edges[r + 1]] = first_region + r
-    return out
+        edges = [0] + bounds + [L]
+        out = np.zeros(L, np.int64)
+        for r in range(7):
+            out[edges[r]:edges[r + 1]] = (0 if kind == 'H' else 7) + r
+        return slice(0, L), out
+    try:
+        start, end, reg = assign_regions(chain['str_seq'], chain['resseq'], kind)
+    except NumberingError as e:
+        raise SystemExit(f'design.py: cannot locate the IMGT regions of the {"heavy" if kind == "H" else "light"} chain ({e}); '
+                         'ANARCI is not available offline — give the CDRs in a <pdb_file>.cdr.json sidecar')
+    return slice(start, end), reg
 
 
 def load_batches(args):
@@ -45,13 +45,16 @@ def load_batches(args):
     side = args.pdb_file + '.cdr.json'
     ranges = json.load(open(side)) if os.path.exists(side) else {}
     H, Lc = chains[h_id], chains[l_id]
+    (hs, h_reg), (ls, l_reg) = _domain(H, 'H', ranges.get('H')), _domain(Lc, 'L', ranges.get('L'))
+    H = {k: v[hs] for k, v in H.items()}                       # variable domains only (make_ab_data_from_mmcif.py:152)
+    Lc = {k: v[ls] for k, v in Lc.items()}
     ags = [chains[c] for c in ag_ids if c in chains]
     rec = dict(
         antibody_str_seq=H['str_seq'] + Lc['str_seq'],
         antibody_coords=np.concatenate([H['coords'], Lc['coords']]), antibody_coord_mask=np.concatenate([H['coord_mask'], Lc['coord_mask']]),
         antibody_chain_ids=np.concatenate([np.zeros(len(H['str_seq']), np.int64), np.ones(len(Lc['str_seq']), np.int64)]),
         antibody_residx=np.concatenate([np.arange(len(H['str_seq'])), np.arange(len(Lc['str_seq'])) + 512]),
-        antibody_cdr_def=np.concatenate([_cdr_def(H, 0, ranges.get('H')), _cdr_def(Lc, 7, ranges.get('L'))]),
+        antibody_cdr_def=np.concatenate([h_reg, l_reg]),
         antigen_str_seq=''.join(a['str_seq'] for a in ags),
         antigen_coords=np.concatenate([a['coords'] for a in ags]) if ags else np.zeros((0, 14, 3), np.float32),
         antigen_coord_mask=np.concatenate([a['coord_mask'] for a in ags]) if ags else np.zeros((0, 14), bool),

@@ -210,24 +210,28 @@ typedef struct {
 #define ABX_IPA_C 256
 #define ABX_IPA_CZ 128
 #define ABX_IPA_FEAT 2112   /* H*(16 + 8*3 + 8 + Cz) */
+#define ABX_IPA_BIAS_ROW 100 /* floats per (key chunk, query row) of the chunked pair bias: 8 keys x 12 heads + 4 pad */
 
 /* bytes of workspace abx_ipa_forward / abx_ipa_attention_features need for a [B,N] problem (upper bound:
  * includes room for the pair-bias tensor used when pair_bias == NULL) */
 size_t abx_ipa_workspace_bytes(int B, int N);
 
-/* pair_bias[b,h,i,j] = sqrt(1/3) * (z[b,i,j,:] . w_pair[h,:] + b_pair[h]) — folding.py:101-104.
+/* sqrt(1/3) * (z[b,i,j,:] . w_pair[h,:] + b_pair[h]) — folding.py:101-104 — in the chunked key-major layout the
+ * fused attention kernel streams with one bulk copy per (tile of query rows, chunk of 8 keys):
+ *   pair_bias[b][j / 8][i][12 (j % 8) + h],  shape [B, ceil(N/8), N, ABX_IPA_BIAS_ROW]  (abx_ipa_pair_bias_floats floats)
  * Depends only on z and the weights, so IpaScore (score_network.py:126-163, 8 weight-shared
  * iterations over the same pair activations) evaluates it once per call. */
+size_t abx_ipa_pair_bias_floats(int B, int N);
 int abx_ipa_pair_bias(void* stream, int B, int N, const float* z, const float* w_pair, const float* b_pair,
-                      float* pair_bias /* [B,H,N,N] */);
+                      float* pair_bias);
 
 /* InvariantPointAttention.forward (folding.py:47-132).
  *   x [B,N,C]; z [B,N,N,Cz]; mask [B,N] f32; rots [B,N,3,3]; trans [B,N,3] (already / position_scale)
- *   pair_bias: [B,H,N,N] from abx_ipa_pair_bias, or NULL (then computed into the workspace)
+ *   pair_bias: the tensor written by abx_ipa_pair_bias, or NULL (then computed into the workspace)
  *   residual: optional [B,N,C] added to the output (score_network.py:128: seq_act += attn)
  *   out [B,N,C]
- * Limits: 1 <= N <= 1536 (ABX_ERR_INVALID beyond; the tensor-core attention kernel serves N <= 640, the SIMT one the
- * rest); x and z 16-byte aligned.  The kernels of one call are chained with programmatic dependent launch on `stream`. */
+ * Limits: 1 <= N <= 1536 (ABX_ERR_INVALID beyond); x, z and pair_bias 16-byte aligned.  The kernels of one call are
+ * chained with programmatic dependent launch on `stream`. */
 int abx_ipa_forward(void* stream, int B, int N, const float* x, const float* z, const float* mask,
                     const float* rots, const float* trans, const abx_ipa_weights* w, const float* pair_bias,
                     const float* residual, float* out, void* workspace, size_t workspace_bytes);

@@ -133,7 +133,7 @@ def frames_to_atom14(aatype, frames):
     grp = torch.from_numpy(rt.table('restype_atom14_to_rigid_group')).to(aatype.device)[aatype].long()       # [B,N,14]
     a_rot = torch.gather(f_rot, 2, grp[..., None, None].expand(grp.shape + (3, 3)))
     a_trans = torch.gather(f_trans, 2, grp[..., None].expand(grp.shape + (3,)))
-    lit = torch.from_numpy(rt.table('restype_atom14_rigid_group_positions')).to(aatype.device)[aatype]
+    lit = torch.from_numpy(rt.table('restype_atom14_rigid_group_positions')).to(aatype.device)[aatype].to(f_rot.dtype)
     return a_trans + torch.einsum('...rd,...d->...r', a_rot, lit)
 
 

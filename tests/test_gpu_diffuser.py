@@ -279,3 +279,33 @@ def test_no_cpu_fallback(cuda_device):
     g = golden('scores')
     with pytest.raises(AbxError):
         fd.calc_quat_score(g['qt'], g['q0'], g['t_a'])            # CPU tensors
+
+
+@pytest.mark.parametrize('center', [True, False])
+def test_reverse_step_baseline_size_matches_oracle(cuda_device, center):
+    """FullDiffuser.reverse at the benchmark's size (B=8, N=350, the centre-of-mass block reduction over 350 residues)
+    against the CPU oracle with injected noise: residue types bit-exact, frames <= 1e-9 (float64 on both sides)."""
+    from tests.gpu_util import reference_table_diffuser
+    fd = reference_table_diffuser()
+    od = oracle_diffuser()
+    gen = torch.Generator().manual_seed(31)
+    B, N = 8, 350
+    q = torch.randn(B, N, 4, generator=gen, dtype=torch.float64); q = q / q.norm(dim=-1, keepdim=True)
+    rig = torch.cat([q, torch.randn(B, N, 3, generator=gen, dtype=torch.float64) * 15], -1)
+    seq = torch.randint(0, 20, (B, N), generator=gen)
+    mask = (torch.rand(B, N, generator=gen) < 0.1).int()
+    mask[0] = 0; mask[0, 100:112] = 1                                           # an H3-like window
+    mask[1] = 1                                                                 # everything diffused
+    t = torch.full((B,), 0.37, dtype=torch.float64)
+    dt = torch.tensor(1 / 100)
+    rot_score, trans_score = torch.randn(B, N, 3, generator=gen), torch.randn(B, N, 3, generator=gen, dtype=torch.float64)
+    logits = torch.randn(B, N, 20, generator=gen) * 3
+    z_rot, z_trans = torch.randn(B, N, 3, generator=gen), torch.randn(B, N, 3, generator=gen)
+    jumps = torch.poisson(torch.rand(B, N, 20, generator=gen) * 0.2, generator=gen)
+    ref_rig, ref_seq = od.reverse(rig, seq, rot_score, trans_score, logits, t, dt, mask, z_rot, z_trans, jumps, center=center)
+    c = lambda x: x.cuda()
+    out, seq1 = fd.reverse(c(rig), c(seq), c(rot_score), c(trans_score), c(logits), c(t), dt, diffuse_mask=c(mask), center=center,
+                           noise=(c(z_rot), c(z_trans), c(jumps)))
+    assert out.dtype == torch.float64
+    assert torch.equal(seq1.cpu(), ref_seq.long())
+    assert maxabs(out.cpu(), ref_rig) < 1e-9

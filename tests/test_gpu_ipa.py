@@ -21,6 +21,13 @@ def make_ipa():
     return ipa.cuda().eval(), P
 
 
+def unchunk_bias(bias, B, N):
+    """Chunked key-major pair bias [B, ceil(N/8), N, 100] (include/abx_b200.h) -> head-major [B,12,N,N]."""
+    nc = (N + 7) // 8
+    t = bias.view(B, nc, N, 100)[..., :96].reshape(B, nc, N, 8, 12)
+    return t.permute(0, 4, 2, 1, 3).reshape(B, 12, N, nc * 8)[..., :N]
+
+
 def test_linear_matches_torch(cuda_device):
     import ctypes
     from abx_b200 import lib
@@ -70,7 +77,31 @@ def test_ipa_matches_oracle(cuda_device, B, N):
     assert maxabs(out.cpu(), ref) < 3e-5 * float(ref.abs().max())
     assert maxabs(out_b.cpu(), ref + x) < 3e-5 * float((ref + x).abs().max())
     ref_bias = (3 ** -0.5) * M.linear(P, PREFIX + 'proj_pair', z).permute(0, 3, 1, 2)
-    assert maxabs(bias.cpu(), ref_bias) < 1e-5 * float(ref_bias.abs().max())
+    assert maxabs(unchunk_bias(bias.cpu(), B, N), ref_bias) < 1e-5 * float(ref_bias.abs().max())
+
+
+@pytest.mark.parametrize('B,N', [(2, 45), (1, 350)])
+def test_ipa_reference_point_moves(cuda_device, B, N):
+    """The fused kernel fixes each (row, head)'s softmax reference point in the first key chunk and moves it only when a
+    later logit exceeds it by 2^64 (accumulators in tensor memory / registers are then rescaled).  Exercise both ways it
+    moves: the first chunks fully masked (reference point -FLT_MAX -> first real logit), and far-away leading keys whose
+    point-distance term puts them > 64 log-2 units below a later key."""
+    ipa, P = make_ipa()
+    gen = torch.Generator().manual_seed(900 + N)
+    x, z = np_randn(910 + N, B, N, 256), np_randn(920 + N, B, N, N, 128)
+    q = torch.randn(B, N, 4, generator=gen); q = q / q.norm(dim=-1, keepdim=True)
+    rots, trans = Q.quat_to_rot(q), torch.randn(B, N, 3, generator=gen) * 2.0
+    trans[:, :11] += 60.0                          # keys 0-10 sit ~100 units away from every other residue
+    mask = torch.ones(B, N)
+    mask[0, :19] = 0                               # leading masked keys on batch element 0 (two full chunks + 3)
+    mask[0, 30] = 0
+    ref, parts = M.ipa_forward(P, x, z, mask, rots, trans, return_parts=True)
+    with torch.no_grad():
+        args = (x.cuda(), z.cuda(), mask.cuda(), (rots.cuda(), trans.cuda()))
+        feats = ipa.attention_features(*args)
+        out = ipa(*args)
+    assert maxabs(feats.cpu(), parts['feats']) < 3e-5 * float(parts['feats'].abs().max())
+    assert maxabs(out.cpu(), ref) < 3e-5 * float(ref.abs().max())
 
 
 def test_ipa_is_frame_invariant(cuda_device):

@@ -271,3 +271,73 @@ def test_full_size_sampler_properties(cuda_device):
     assert torch.equal(seq[fixed[:, :n_ab]], batch['seq_t'].cpu()[:, :n_ab][fixed[:, :n_ab]].clamp(0, 19))
     assert torch.equal(outs[0][1], outs[1][1]) and maxabs(outs[0][0], outs[1][0]) < 1e-3   # same seed
     assert maxabs(outs[0][2][~fixed], outs[2][2][~fixed]) > 1e-2                            # other seed, other frames
+
+
+def _pair_digest(pair, pos):
+    p = pair[0]
+    return dict(samples=p[pos[:, 0], pos[:, 1]], row_sum=p.sum(dim=1), col_sum=p.sum(dim=0))
+
+
+@pytest.mark.parametrize('name', ['model_n350', 'model_n262'])
+def test_baseline_size_error_budget(cuda_device, name):
+    """BASELINE-size parity (N = 350 synthetic north-star complex, N = 262 real-size stand-in) with a MEASURED error budget.
+
+    tests/golden/model_n*.npz (oracle/make_golden.py gen_big) holds, for the same inputs and seeded weights,
+      r32_*  the reference's own modules in float32,
+      o64_*  the oracle evaluated in float64 = the value the float32 arithmetic approximates.
+    |r32 - o64| is the reference's own float32 noise.  A correct float32 implementation cannot be closer to r32 than that
+    noise, so the bars are: (a) one trunk pass and IpaScore, the modules north_star's 1e-4 applies to: |gpu - r32| <= 1e-4
+    (relative to the tensor's scale for activations, absolute for frames), on the FULL tensors (pair activations through
+    1536 sampled positions + row / column sums, which move under any transposed or tile-local indexing error);
+    (b) the whole ScoreNetwork.forward (3 chained trunk passes + 24 IPA layers): |gpu - o64| <= 3 |r32 - o64| + 1e-4,
+    i.e. the product is as close to the exact arithmetic as the reference itself, up to a small factor."""
+    from tests.gpu_util import reference_table_diffuser
+    g = golden(name)
+    model = make_model(reference_table_diffuser())
+    batch = to_cuda(batch_from_golden(g))
+    B, N = batch['seq'].shape
+    pos = g['pair_pos'].long()
+    report = {}
+
+    def budget(key, gpu, rel=False):
+        r32, o64 = g['r32_' + key].double(), g['o64_' + key].double()
+        scale = max(1.0, float(o64.abs().max())) if rel else 1.0
+        e_ref, e_gpu, d = maxabs(r32, o64) / scale, maxabs(gpu.cpu(), o64) / scale, maxabs(gpu.cpu(), r32) / scale
+        report[key] = dict(ref_vs_f64=e_ref, gpu_vs_f64=e_gpu, gpu_vs_ref=d)
+        return e_ref, e_gpu, d
+
+    b1 = dict(batch)
+    b1.update(prev_pos=torch.zeros(B, N, N, dtype=torch.int64, device='cuda'), prev_seq=torch.zeros(B, N, 544, device='cuda'),
+              prev_pair=torch.zeros(B, N, N, 192, device='cuda'), is_recycling=True)
+    rep = {'seq': np_randn(921, B, N, 544).cuda(), 'pair': np_randn(922, B, N, N, 192).cuda()}
+    with torch.no_grad():
+        s, p = model.impl.seqformer(b1)
+        ipa = model.impl.diffusion_module.ScoreNetwork(rep, dict(batch))
+        bm = dict(batch)
+        out = model(bm)
+    # (a) single trunk pass, full tensors
+    assert budget('trunk_seq', s, rel=True)[2] < 1e-4
+    for k, v in _pair_digest(p.cpu(), pos).items():
+        n_terms = 1 if k == 'samples' else N
+        assert budget('trunk_pair_' + k, v, rel=True)[2] < 1e-4 * n_terms ** 0.5, k
+    # (a) IpaScore on seeded representations
+    assert budget('ipa_structure_module', ipa['representations']['structure_module'], rel=True)[2] < 1e-4
+    assert budget('ipa_rigids', ipa['rigids'])[2] < 1e-4                         # Angstrom / quaternion components
+    assert budget('ipa_angles', ipa['sidechains'][-1]['angles_sin_cos'])[2] < 1e-4
+    assert budget('ipa_trans_score', ipa['trans_score'])[2] < 1e-4
+    # (b) the whole network against the float64 value
+    h = out['heads']
+    assert torch.equal(h['sequence_module']['seq_0'].cpu(), g['r32_seq_0'])
+    assert torch.equal(bm['seq_t'].cpu(), g['r32_seq_t_after'])
+    full = dict(rigids=h['folding']['rigids'], atom14=h['folding']['final_atom14_positions'],
+                trans_score=h['folding']['trans_score'], logits=h['sequence_module']['logits'],
+                pLDDT=h['predicted_lddt']['pLDDT'], rep_seq=out['representations']['seq'])
+    for k, v in full.items():
+        e_ref, e_gpu, _ = budget(k, v)
+        assert e_gpu < 3 * e_ref + 1e-4, (k, e_ref, e_gpu)
+    for k, v in _pair_digest(out['representations']['pair'].cpu(), pos).items():
+        e_ref, e_gpu, _ = budget('rep_pair_' + k, v)
+        assert e_gpu < 3 * e_ref + 1e-4 * (1 if k == 'samples' else N ** 0.5), (k, e_ref, e_gpu)
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', f'error_budget_{name}.json'), 'w') as f:
+        json.dump(report, f, indent=1)
