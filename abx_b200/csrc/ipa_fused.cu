@@ -56,7 +56,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr int kZSlotBytes = kChunk * kCz * 4; // 4096
 constexpr int kKVChunkBytes = kChunk * kKVRow * 4;    // 26112
 constexpr int kThreads = 896;
-constexpr int kRegsCtl = 40, kRegsConv = 48, kRegsSvc = 56, kRegsLogit = 128, kRegsVal = 96;
+constexpr int kRegsCtl = 40, kRegsConv = 40, kRegsSvc = 48, kRegsLogit = 128, kRegsVal = 96;   // 62464 of 65536
 static_assert(128 * kRegsCtl + 256 * kRegsConv + 128 * kRegsSvc + 128 * kRegsLogit + 256 * kRegsVal <= 65536, "register budget");
 constexpr int kFeatPt = kH * kSv, kFeatNorm = kFeatPt + 3 * kH * kPv, kFeatPair = kFeatNorm + kH * kPv;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -97,15 +97,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Watchdog: a wait that spins for more than ~0.25 s records (tag, block, thread, parity) in g_ipa_watchdog and raises the
+// abort flag; every wait of every CTA then returns at once, so a synchronisation bug ends the kernel (with garbage results and
+// a readable record, abx_ipa_watchdog_read) instead of hanging the device.
+__device__ unsigned long long g_ipa_watchdog[8];
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  if (ok) return;
+  const long long t0 = clock64();
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok) {
+      if (*reinterpret_cast<volatile unsigned long long*>(&g_ipa_watchdog[0]) != 0ull) return;
+      if (clock64() - t0 > 500000000ll) {
+        if (atomicCAS(&g_ipa_watchdog[0], 0ull, 1ull) == 0ull) {
+          g_ipa_watchdog[1] = (unsigned long long)tag;
+          g_ipa_watchdog[2] = blockIdx.x;
+          g_ipa_watchdog[3] = threadIdx.x;
+          g_ipa_watchdog[4] = parity;
+          __threadfence();
+        }
+        return;
+      }
+    }
   } while (!ok);
 }
 // global -> shared bulk copy (bytes and both addresses multiples of 16) completing on an mbarrier
@@ -306,7 +330,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t bytes = (uint32_t)min(kChunk, N - c * kChunk) * kCz * 4;
         for (int r = 0; r < nvalid; ++r) {
-          mbar_wait(z_empty + slot, ph);
+          mbar_wait(z_empty + slot, ph, 101);
           mbar_expect_tx(z_full + slot, bytes);
           bulk_g2s(ZR + (size_t)slot * kZSlotBytes, zb + (size_t)r * row_bytes + (size_t)c * kZSlotBytes, bytes, z_full + slot);
           if (++slot == zslots) { slot = 0; ph ^= 1; }
@@ -317,7 +341,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       griddep_wait();                                // Qp / KVp come from the kernels launched just before
       for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1, nk = min(kChunk, N - c * kChunk);
-        mbar_wait(kv_empty + buf, ((c >> 1) & 1) ^ 1);
+        mbar_wait(kv_empty + buf, ((c >> 1) & 1) ^ 1, 201);
         const uint32_t kvb = (uint32_t)nk * kKVRow * 4, bb = (uint32_t)nvalid * kBiasRow * 4;
         mbar_expect_tx(kv_full + buf, kvb + bb);
         bulk_g2s(KVs + (size_t)buf * kChunk * kKVRow, KVp + ((size_t)b * N + c * kChunk) * kKVRow, kvb, kv_full + buf);
@@ -331,18 +355,18 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
         uint32_t aph = 0;
         for (int c = 0; c < nchunks; ++c) {
           const int pb = c % kPD;
-          mbar_wait(p_full + pb, (c / kPD) & 1);
+          mbar_wait(p_full + pb, (c / kPD) & 1, 301);
           tc_fence_after();
           const unsigned rm = *reinterpret_cast<volatile unsigned*>(resc + (c & 3));
           for (int r = 0; r < nvalid; ++r, ++k) {
-            mbar_wait(a_full + aslot, aph);
+            mbar_wait(a_full + aslot, aph, 302);
             tc_fence_after();
             if ((rm >> r) & 1u) {                    // the reference point of some head of row r moved: rescale D_r first
               umma_commit(drain);
-              mbar_wait(drain, dr); dr ^= 1;
+              mbar_wait(drain, dr, 303); dr ^= 1;
               req_info[0] = r; req_info[1] = pb;
               mbar_arrive(req);
-              mbar_wait(resp, rs); rs ^= 1;
+              mbar_wait(resp, rs, 304); rs ^= 1;
               tc_fence_after();
             }
             const uint32_t d = tmem_base + 16u * r;
@@ -358,7 +382,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
           umma_commit(p_empty + pb);                 // probability tiles of the chunk consumed
         }
         umma_commit(drain);
-        mbar_wait(drain, dr);
+        mbar_wait(drain, dr, 305);
         req_info[0] = -1; req_info[1] = 0;
         mbar_arrive(req);
       }
@@ -375,7 +399,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     for (int k = cw; k < nitems; k += 2) {
       const int zs = k % zslots, as = k % kASlots;
       const int nk = min(kChunk, N - c * kChunk);
-      mbar_wait(z_full + zs, (uint32_t)(k / zslots) & 1u);
+      mbar_wait(z_full + zs, (uint32_t)(k / zslots) & 1u, 401);
       const float* zp = reinterpret_cast<const float*>(ZR + (size_t)zs * kZSlotBytes) + ch;
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -391,7 +415,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
         lo[kk] = __float_as_uint(__uint_as_float(hi[kk]) - __uint_as_float(hi[kk] & 0xffffe000u));
       __syncwarp();                                  // every lane has read the z slot
       if (lane == 0) mbar_arrive(z_empty + zs);
-      mbar_wait(a_empty + as, ((uint32_t)(k / kASlots) & 1u) ^ 1u);
+      mbar_wait(a_empty + as, ((uint32_t)(k / kASlots) & 1u) ^ 1u, 402);
       tc_fence_after();
       tmem_st8(lane_base + 16u * as, hi);
       tmem_st8(lane_base + 16u * as + 8u, lo);
@@ -412,7 +436,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
     uint32_t ph = 0;
     for (;;) {
-      mbar_wait(req, ph); ph ^= 1;
+      mbar_wait(req, ph, 501); ph ^= 1;
       const int r = req_info[0], pb = req_info[1];
       if (r < 0) break;
       tc_fence_after();
@@ -428,7 +452,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       if (lane == 0) mbar_arrive(resp);
     }
     tc_fence_after();
-    mbar_wait(lsum_ready, 0);
+    mbar_wait(lsum_ready, 0, 502);
     for (int r = 0; r < nvalid; ++r) {
       uint32_t v[16];
       tmem_ld16(lane_base + 16u * r, v);
@@ -467,8 +491,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
 
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1, pb = c % kPD, j0 = c * kChunk;
-      mbar_wait(kv_full + buf, (c >> 1) & 1);
-      mbar_wait(p_empty + pb, ((c / kPD) & 1) ^ 1);
+      mbar_wait(kv_full + buf, (c >> 1) & 1, 601);
+      mbar_wait(p_empty + pb, ((c / kPD) & 1) ^ 1, 602);
       if (t == 0) resc[(c + 2) & 3] = 0u;
       const float* kvp = KVs + (size_t)buf * kChunk * kKVRow + h * kQK;
       const float* bs0 = BSs + ((size_t)buf * kMaxRows + r0) * kBiasRow + h;
@@ -564,8 +588,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
 
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1, pb = c % kPD, nk = min(kChunk, N - c * kChunk);
-      mbar_wait(kv_full + buf, (c >> 1) & 1);
-      mbar_wait(p_full + pb, (c / kPD) & 1);
+      mbar_wait(kv_full + buf, (c >> 1) & 1, 701);
+      mbar_wait(p_full + pb, (c / kPD) & 1, 702);
       {
         const float4* ap = reinterpret_cast<const float4*>(AL + ((size_t)pb * kH + h) * kPfRow + rg * 12);
         const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
@@ -602,7 +626,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     }
 
     // ---- normalise, stage the 480 value outputs of every row, then write o_scalar / o_point / o_point_norm ----
-    mbar_wait(lsum_ready, 0);
+    mbar_wait(lsum_ready, 0, 703);
     asm volatile("bar.sync 1, 256;" ::: "memory");   // every value warp is done with the key/value buffers
     float* OV = reinterpret_cast<float*>(sm + L.ov); // [R][480]
     if (worker) {
@@ -720,6 +744,15 @@ static int fused_sm_count() {
     return v;
   }();
   return n;
+}
+
+// copies and clears the watchdog record: out[0] != 0 -> a wait timed out; out[1..4] = tag, block, thread, parity
+int ipa_watchdog_read(unsigned long long* out) {
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("ipa_watchdog_read: %s", cudaGetErrorString(cudaGetLastError())); return ABX_ERR_CUDA; }
+  ABX_CUDA(cudaMemcpyFromSymbol(out, g_ipa_watchdog, sizeof(zero)));
+  ABX_CUDA(cudaMemcpyToSymbol(g_ipa_watchdog, zero, sizeof(zero)));
+  return ABX_OK;
 }
 
 size_t ipa_fused_qp_floats(int B, int N) { return (size_t)B * N * kQRow; }

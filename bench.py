@@ -10,8 +10,9 @@ ScoreNetwork forwards = 2424 IPA layer-calls; default 8 samples per GPU per step
 complex (weak scaling, no data-path collective; inputs are broadcast from rank 0 once and the designed
 coordinates are gathered to rank 0 every step).
 
-Prints ONE JSON line on rank 0.  `--impl reference` times the CPU oracle (the restatement of the
-reference's PyTorch code, oracle/) on the host cores on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.  `--impl reference` times the reference's own PyTorch-CPU modules (oracle/_ref,
+materialised from the reference checkout by oracle/build_ref.py; kind "reference") on the host cores on a bounded
+sample of the same workload — or, when oracle/_ref did not travel, the CPU oracle restatement (kind "port").
 """
 import argparse
 import json
@@ -171,21 +172,54 @@ def cpu_oracle_rate(a, cfg, score_norms=None, threads=None):
                       f'of the T={a.num_t} loop at N={N}, batch 1, float32 torch-CPU oracle; extrapolated x({a.num_t + 1}, {a.num_t - 1})'}
 
 
+def reference_rate(a, iterations, warm_iterations=0, threads=None, budget_s=240.0):
+    """samples/s of the REFERENCE's own modules (oracle/_ref, materialised from the reference checkout by
+    oracle/build_ref.py) on this host: the self-conditioning warm-up call, `warm_iterations` untimed and `iterations`
+    timed iterations of the reverse loop (ScoreNetwork.forward + get_prev + FullDiffuser.reverse, inference.py:213-251) at
+    the benchmark's N, batch 1 (the reference's operating point); per-iteration cost does not depend on t, so
+    samples/s = 1 / ((T+1) t_model + (T-1) t_reverse).  Stops early once `budget_s` of host time is spent."""
+    from oracle import ref_runner
+    threads = threads or os.cpu_count() or 1
+    loop = ref_runner.ReferenceLoop(a.n_antigen, a.num_t, threads)
+    t_start = time.perf_counter()
+    tm, tr = [], []
+    for i in range(warm_iterations + iterations):
+        m, r = loop.step()
+        if i >= warm_iterations:
+            tm.append(m); tr.append(r)
+        if time.perf_counter() - t_start > budget_s and len(tm) >= 1:
+            break
+    if not tm:
+        tm, tr = [m], [r]
+    mm, mr = statistics.mean(tm), statistics.mean(tr)
+    rate = 1.0 / ((a.num_t + 1) * mm + (a.num_t - 1) * mr)
+    return {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'reference',
+            'sample': f'{len(tm)} iterations of the reference\'s own reverse loop (ScoreNetwork.forward + get_prev {mm:.2f} s, '
+                      f'FullDiffuser.reverse {mr * 1e3:.1f} ms each) after the self-conditioning call and {warm_iterations} untimed '
+                      f'iterations, N={loop.n_res}, batch 1, float32 torch-CPU; extrapolated x({a.num_t + 1}, {a.num_t - 1})'}
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cfg = model_config()
-    vals = []
-    base = None
-    for i in range(a.warmup + a.steps):
-        base = cpu_oracle_rate(a, cfg)
-        if i >= a.warmup:
-            vals.append(base['value'])
-        if i == 0 and a.warmup + a.steps > 1 and 1.0 / base['value'] / (a.num_t + 1) > 20:
-            break                      # very slow host: one bounded sample is all a few minutes allow
-    if not vals:
+    from oracle import ref_runner
+    if ref_runner.available():
+        # one bench "step" = one iteration of the reference's reverse loop (a bounded sample of the 100-step workload)
+        base = reference_rate(a, iterations=max(a.steps, 3), warm_iterations=min(a.warmup, 3))
         vals = [base['value']]
+    else:
+        vals = []
+        base = None
+        for i in range(a.warmup + a.steps):
+            base = cpu_oracle_rate(a, cfg)
+            if i >= a.warmup:
+                vals.append(base['value'])
+            if i == 0 and a.warmup + a.steps > 1 and 1.0 / base['value'] / (a.num_t + 1) > 20:
+                break                      # very slow host: one bounded sample is all a few minutes allow
+        if not vals:
+            vals = [base['value']]
     v = statistics.mean(vals)
     n_res = 230 + a.n_antigen
     base['value'] = v
@@ -254,16 +288,30 @@ def run_b200(a):
 
     resident = features_from_host()
     gather_buf = [torch.empty(S, n_ab, 14, 3, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
-    ipa_events = []
+    ipa_events, bias_events, rev_events, rev_launches = [], [], [], []
     orig_forward = folding.InvariantPointAttention.forward
+    orig_bias = folding.InvariantPointAttention.pair_bias
+    orig_reverse = FullDiffuser.reverse
 
-    def timed_forward(self, *args, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = orig_forward(self, *args, **kw)
-        e1.record()
-        ipa_events.append((e0, e1))
-        return out
+    def _timed(orig, sink, count=None):
+        def wrapper(self, *args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = lib.launch_count()
+            e0.record()
+            out = orig(self, *args, **kw)
+            e1.record()
+            sink.append((e0, e1))
+            if count is not None:
+                count.append(lib.launch_count() - n0)
+            return out
+        return wrapper
+
+    timed_forward = _timed(orig_forward, ipa_events)
+
+    def instrument(on):
+        folding.InvariantPointAttention.forward = timed_forward if on else orig_forward
+        folding.InvariantPointAttention.pair_bias = _timed(orig_bias, bias_events) if on else orig_bias
+        FullDiffuser.reverse = _timed(orig_reverse, rev_events, rev_launches) if on else orig_reverse
 
     use_graph = [bool(a.cuda_graph)]
 
@@ -307,9 +355,9 @@ def run_b200(a):
         clocks.start()
     lib.reset_launch_count()
     if not use_graph[0]:
-        folding.InvariantPointAttention.forward = timed_forward
+        instrument(True)
     ms_total, _ = timed(a.steps, False, a.warmup)
-    folding.InvariantPointAttention.forward = orig_forward
+    instrument(False)
     launches = torch.tensor([lib.launch_count()], device=dev, dtype=torch.int64)
     if use_graph[0]:        # launches recorded while capturing replay once per reverse iteration
         launches = launches + (a.num_t - 2) * getattr(sampler.GraphedReverseStep, 'last_captured_launches', 0) * a.steps
@@ -323,12 +371,21 @@ def run_b200(a):
         # CUDA events cannot be read back from inside a replayed graph: the per-call IPA timing comes from one
         # more step of the same workload run eagerly (same kernels, same shapes) right after the timed region
         use_graph[0] = False
-        folding.InvariantPointAttention.forward = timed_forward
+        instrument(True)
         ms_instr, _ = timed(1, False, a.warmup + 2 * a.steps)
-        folding.InvariantPointAttention.forward = orig_forward
+        instrument(False)
         use_graph[0] = True
     torch.cuda.synchronize()
     ipa_ms = [e0.elapsed_time(e1) for e0, e1 in ipa_events]
+    bias_ms = [e0.elapsed_time(e1) for e0, e1 in bias_events]
+    rev_ms = [e0.elapsed_time(e1) for e0, e1 in rev_events]
+    # K2': wall time of the IGSO(3) table build (so3_diffuser.py:150-181; 72 s of CPU time in the reference)
+    table_s = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fd._so3_diffuser.build_tables(dev)
+        table_s = time.perf_counter() - t0
 
     if rank == 0:
         total_samples = world * S * a.steps
@@ -340,14 +397,23 @@ def run_b200(a):
             pass
         peak = peaks.get('hbm_gbs', 6650.0)
         alg = S * 4 * (128 * n_res * n_res + 2 * 256 * n_res + 12 * n_res + n_res) + 4 * 838552     # SURVEY §8d, per layer-call
-        traffic = None                                   # dram read+write bytes of one layer-call from the committed ncu capture
-        try:
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ipa_traffic.json')))
-            if tr.get('B') == S and tr.get('N') == n_res:
-                traffic = tr['traffic_bytes']
-        except Exception:
-            pass
-        ipa_mean = statistics.mean(ipa_ms)
+        # dram read+write bytes of one layer-call: NOT measured in this run (ncu cannot run inside the bench) — the constant
+        # of the committed `ncu --set full` capture of the same kernels at the same (B, N), profiles/r02_ipa_traffic.json
+        traffic, traffic_source = None, None
+        for fn in ('r02_ipa_traffic.json', 'r01_ipa_traffic.json'):
+            try:
+                tr = json.load(open(os.path.join(ROOT, 'profiles', fn)))
+                if tr.get('B') == S and tr.get('N') == n_res:
+                    traffic, traffic_source = tr['traffic_bytes'], f'constant from profiles/{fn} (ncu --set full capture, not measured in this run)'
+                    break
+            except Exception:
+                pass
+        # one IpaScore call = 1 pair-bias pass (folding.py:101-104; z and the weights are the same in its 8 iterations) + 8
+        # layer-calls: the roofline unit charges every layer-call with 1/8 of the bias pass
+        n_iter = int(cfg['model']['heads']['diffusion_module']['IPA']['num_layer'])      # config_model.json:108
+        ipa_fwd = statistics.mean(ipa_ms)
+        bias_share = (statistics.mean(bias_ms) / n_iter) if bias_ms else 0.0
+        ipa_mean = ipa_fwd + bias_share
         achieved = alg / (ipa_mean * 1e-3) / 1e9
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
@@ -361,14 +427,28 @@ def run_b200(a):
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 (of fallback)',
                          'algorithmic_bytes_per_launch': alg, 'ms_per_launch': ipa_mean, 'launches_timed': len(ipa_ms),
-                         'share_of_step': sum(ipa_ms) / ms_instr,
+                         'ms_layer_call_alone': ipa_fwd, 'ms_pair_bias_pass': statistics.mean(bias_ms) if bias_ms else None,
+                         'pair_bias_passes_timed': len(bias_ms), 'layer_calls_per_bias_pass': n_iter,
+                         'frac_without_bias_pass': alg / (ipa_fwd * 1e-3) / 1e9 / peak,
+                         'share_of_step': (sum(ipa_ms) + sum(bias_ms)) / ms_instr,
                          'timed_in': 'eager instrumented step after the graph-replayed timed region' if a.cuda_graph else 'timed region',
-                         'traffic': traffic},
+                         'traffic': traffic, 'traffic_source': traffic_source},
+            # K2: the reverse step is latency-bound — time per FullDiffuser.reverse call (2 randn + rates +
+            # poisson + the fused SE(3)/categorical step) and this library's launches per call, against ~120 launches and
+            # >= 8 host syncs of the reference's op-by-op step on a GPU
+            'reverse_step': {'us_per_call': 1e3 * statistics.mean(rev_ms) if rev_ms else None, 'calls_timed': len(rev_ms),
+                             'library_launches_per_call': statistics.mean(rev_launches) if rev_launches else None,
+                             'torch_launches_per_call': 3, 'reference_launches_per_call': 120, 'bytes_per_residue': 284},
+            'igso3_table_build': {'seconds': table_s, 'series_terms': 1000 * 1000 * 1000, 'reference_cpu_seconds': 72},
             'clocks': clock_info,
         }
         if not a.no_cpu_baseline:
             try:
-                line['cpu_baseline'] = cpu_oracle_rate(a, cfg, score_norms=fd._so3_diffuser._score_norms)
+                from oracle import ref_runner
+                if ref_runner.available():
+                    line['cpu_baseline'] = reference_rate(a, iterations=max(a.cpu_steps, 2), budget_s=60.0)
+                else:
+                    line['cpu_baseline'] = cpu_oracle_rate(a, cfg, score_norms=fd._so3_diffuser._score_norms)
             except Exception as e:                                   # never lose the GPU numbers to a host-side problem
                 line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {e}'}
         print(json.dumps(line), flush=True)

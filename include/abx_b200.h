@@ -246,6 +246,12 @@ int abx_ipa_frame_update(void* stream, int B, int N, const float* upd, const flo
                          const float* init_trans, const int32_t* fixed_mask, float* delta_quat, float* curr_quats,
                          float* curr_trans, float* curr_rots);
 
+/* Watchdog of the fused attention kernel: every mbarrier wait in it gives up after ~0.25 s of spinning, records where
+ * (out8[1..4] = wait tag, block, thread, parity) and makes all other waits return, so a synchronisation fault ends the
+ * kernel with a readable record instead of hanging the device.  Synchronises the device, copies and clears the record;
+ * out8[0] != 0 means a wait timed out since the last call (the results of that launch are garbage). */
+int abx_ipa_watchdog_read(unsigned long long* out8);
+
 /* Stages of abx_ipa_forward, exported so tests and the benchmark can time/verify them separately. */
 /* feats [B,N,2112] = concat(o_scalar 192, o_point_local (r n) 288, o_point_norm 96, o_pair 1536) */
 int abx_ipa_attention_features(void* stream, int B, int N, const float* x, const float* z, const float* mask,
