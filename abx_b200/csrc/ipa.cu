@@ -513,6 +513,7 @@ size_t ipa_fused_qp_floats(int B, int N);
 size_t ipa_fused_kvp_floats(int B, int N);
 size_t ipa_pair_bias_floats(int B, int N);
 int ipa_watchdog_read(unsigned long long* out);
+int ipa_prof(int enable, unsigned long long* out64);
 int launch_ipa_pair_bias(cudaStream_t s, int B, int N, const float* z, const float* w_pair, const float* b_pair, float* bias);
 int launch_ipa_pack_nodes(cudaStream_t s, int B, int N, const float* proj, const float* rots, const float* trans, float* Qp,
                           float* KVp);
@@ -675,6 +676,8 @@ extern "C" int abx_ipa_watchdog_read(unsigned long long* out8) {
   ABX_REQUIRE(out8 != nullptr, "abx_ipa_watchdog_read: null argument");
   return ipa_watchdog_read(out8);
 }
+
+extern "C" int abx_ipa_profile(int enable, unsigned long long* out64) { return ipa_prof(enable, out64); }
 
 extern "C" size_t abx_ipa_pair_bias_floats(int B, int N) {
   if (B <= 0 || N <= 0) return 0;

@@ -15,16 +15,16 @@
 // One CTA (28 warps, register budgets re-balanced with setmaxnreg) = a tile of R <= 20 query rows of one batch
 // element; it walks the keys in chunks of 8 with every row in lock step, so the chunk's packed key / value operands
 // (26 KB, one bulk copy, served by L2) are shared by the R rows.  Roles:
-//   warp 0        z producer: one 4 KB cp.async.bulk per (row, chunk) "item" into a shared-memory ring (mbarrier tx counts)
-//   warp 2        key/value + pair-bias producer (double-buffered chunk, two bulk copies)
-//   warps 4-11    two converter warpgroups (alternating items): thread = channel reads the item's 8 keys, splits hi / lo,
-//                 tcgen05.st into a 12-slot A ring in tensor memory, releases the z slot
+//   warp 0        z producer: lane r issues one 4 KB cp.async.bulk per chunk for query row r — a (row, chunk) "item" — into a
+//                 shared-memory ring (mbarrier tx counts); lane 31: key/value + pair-bias producer (double-buffered chunk)
+//   warps 4-11    two converter warpgroups (alternating pairs of items): thread = channel reads the item's 8 keys, splits
+//                 hi / lo, tcgen05.st into a 12-slot A ring in tensor memory, releases the z slot
 //   warps 16-19   logits + online softmax: thread = (head, 2 query rows) with its queries in registers, all 8 keys of the
 //                 chunk; exact fp32 FFMA2 arithmetic.  The softmax reference point m is fixed by the first chunk and only
 //                 moves when a later logit exceeds it by 2^64 (flagged, see below), so accumulators are never rescaled in
 //                 the common case.  Writes p (hi / lo MMA operand tiles + a plain copy for the value warps).
 //   warps 20-27   attention over the 40-wide value rows: thread = (10 query rows x 4 value dims) register tile
-//   warp 1        MMA issuer: per item 3 x tcgen05.mma (hi*lo, lo*hi, hi*hi), commit -> frees the A slot
+//   warps 1-3     MMA issuers (query rows mod 3): per item 3 x tcgen05.mma (hi*lo, lo*hi, hi*hi), commit -> frees the A slot
 //   warps 12-15   accumulator service: rescales D_i in tensor memory when a reference point moved (rare), and at the end
 //                 reads D (tcgen05.ld), normalises by the row sums and writes o_pair
 // The pair bias sqrt(1/3)(z W^T + b) is read from the chunked key-major tensor written by ipa_pair_bias_kernel
@@ -56,13 +56,14 @@ constexpr uint32_t kTmemCols = 512;
 constexpr int kZSlotBytes = kChunk * kCz * 4; // 4096
 constexpr int kKVChunkBytes = kChunk * kKVRow * 4;    // 26112
 constexpr int kThreads = 896;
+constexpr int kIssuers = 3;                   // MMA issuer warps (query rows interleaved)
 constexpr int kRegsCtl = 40, kRegsConv = 40, kRegsSvc = 48, kRegsLogit = 128, kRegsVal = 96;   // 62464 of 65536
 static_assert(128 * kRegsCtl + 256 * kRegsConv + 128 * kRegsSvc + 128 * kRegsLogit + 256 * kRegsVal <= 65536, "register budget");
 constexpr int kFeatPt = kH * kSv, kFeatNorm = kFeatPt + 3 * kH * kPv, kFeatPair = kFeatNorm + kH * kPv;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleGap = 64.f;           // log2 units: the reference point moves when a logit exceeds it by this much
 
-enum Warps { kWarpZ = 0, kWarpMma = 1, kWarpKV = 2, kWarpConv0 = 4, kWarpSvc = 12, kWarpLogit = 16, kWarpVal = 20 };
+enum Warps { kWarpZ = 0, kWarpMma = 1, kWarpConv0 = 4, kWarpSvc = 12, kWarpLogit = 16, kWarpVal = 20 };
 
 // ---- shared-memory carve-up (byte offsets from a 128-byte aligned base) ----
 struct Smem {
@@ -101,16 +102,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // abort flag; every wait of every CTA then returns at once, so a synchronisation bug ends the kernel (with garbage results and
 // a readable record, abx_ipa_watchdog_read) instead of hanging the device.
 __device__ unsigned long long g_ipa_watchdog[8];
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+__device__ unsigned long long g_ipa_prof[64];
+template <bool kSleep = false>
+__device__ __forceinline__ long long mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {   // returns the cycles spent spinning
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
+  const long long t0 = clock64();                  // try_wait itself blocks for a while: time the first attempt too
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-  if (ok) return;
-  const long long t0 = clock64();
+  if (ok) return clock64() - t0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -118,7 +121,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     if (!ok) {
-      if (*reinterpret_cast<volatile unsigned long long*>(&g_ipa_watchdog[0]) != 0ull) return;
+      if (kSleep) __nanosleep(1000);                 // long idle waits (accumulator service) stay off the issue slots
+      if (*reinterpret_cast<volatile unsigned long long*>(&g_ipa_watchdog[0]) != 0ull) return clock64() - t0;
       if (clock64() - t0 > 500000000ll) {
         if (atomicCAS(&g_ipa_watchdog[0], 0ull, 1ull) == 0ull) {
           g_ipa_watchdog[1] = (unsigned long long)tag;
@@ -127,11 +131,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
           g_ipa_watchdog[4] = parity;
           __threadfence();
         }
-        return;
+        return clock64() - t0;
       }
     }
   } while (!ok);
+  return clock64() - t0;
 }
+
+// optional per-role stall profile (tools/bench_ipa.py --prof): cycles of every role's main loop and of its two waits, summed
+// over the CTAs, at prof[8 role + {0: loop, 1: first wait, 2: second wait, 3: contributors}]
+struct RoleProf {
+  long long t0, w[2];
+  __device__ __forceinline__ void start() { t0 = clock64(); w[0] = w[1] = 0; }
+  __device__ __forceinline__ void flush(unsigned long long* prof, int role) {
+    if (prof == nullptr) return;
+    atomicAdd(prof + 8 * role + 0, (unsigned long long)(clock64() - t0));
+    atomicAdd(prof + 8 * role + 1, (unsigned long long)w[0]);
+    atomicAdd(prof + 8 * role + 2, (unsigned long long)w[1]);
+    atomicAdd(prof + 8 * role + 3, 1ull);
+  }
+};
 // global -> shared bulk copy (bytes and both addresses multiples of 16) completing on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -188,6 +207,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ int pf_row(int r) { return r + 2 * (r / kHalfRows); }
@@ -257,9 +286,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restrict__ Qp, const float* __restrict__ KVp,
                  const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
                  const float* __restrict__ trans, const float* __restrict__ point_weights, const float* __restrict__ z,
-                 float* __restrict__ feats) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+                 float* __restrict__ feats, unsigned long long* __restrict__ prof) {
+  // no swizzled operand tiles here: 16-byte alignment (bulk copies, descriptors) is all the carve-up needs, so the dynamic
+  // shared array is used as is and every access below stays a shared-state-space instruction (LDS / STS)
+  extern __shared__ __align__(128) uint8_t sm[];
   const Smem L = smem_layout(N, zslots);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x / tiles_per_b, i0 = (blockIdx.x % tiles_per_b) * R;
@@ -279,26 +309,30 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   uint64_t* kv_full = bars;                         // [2]
   uint64_t* kv_empty = bars + 2;                    // [2]  4 logit warps + 8 value warps
   uint64_t* p_full = bars + 4;                      // [kPD] 4 logit warps
-  uint64_t* p_empty = bars + 6;                     // [kPD] MMA commit + 8 value warps
+  uint64_t* p_empty = bars + 6;                     // [kPD] MMA issuers' commits + 8 value warps
   uint64_t* a_full = bars + 8;                      // [12] 4 converter warps
   uint64_t* a_empty = bars + 20;                    // [12] MMA commit
   uint64_t* req = bars + 32;                        // MMA -> accumulator service
   uint64_t* resp = bars + 33;                       // 4 service warps -> MMA
-  uint64_t* drain = bars + 34;                      // MMA commit: everything issued so far has completed
-  uint64_t* lsum_ready = bars + 35;                 // 4 logit warps: LINV is final
+  uint64_t* drain = bars + 34;                      // [kIssuers] issuer's commit: everything it issued so far has completed
+  uint64_t* lsum_ready = bars + 37;                 // 4 logit warps: LINV is final
   uint64_t* z_full = bars + 40;                     // [zslots]
   uint64_t* z_empty = z_full + zslots;              // [zslots] 4 converter warps
   volatile int* req_info = reinterpret_cast<volatile int*>(z_empty + zslots);    // {row or -1, probability buffer}
   unsigned* resc = reinterpret_cast<unsigned*>(const_cast<int*>(req_info) + 2);  // [4] rows whose reference point moved in chunk c & 3
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resc + 4);
+  unsigned* svc_lock = resc + 4;                    // issuers take turns talking to the accumulator service
+  unsigned* svc_phase = resc + 5;                   // number of rescale requests served so far (parity of `resp`)
+  unsigned* issuers_done = resc + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resc + 8);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 12); }
-    for (int s = 0; s < kPD; ++s) { mbar_init(p_full + s, 4); mbar_init(p_empty + s, 9); }
+    for (int s = 0; s < kPD; ++s) { mbar_init(p_full + s, 4); mbar_init(p_empty + s, 8 + kIssuers); }
     for (int s = 0; s < kASlots; ++s) { mbar_init(a_full + s, 4); mbar_init(a_empty + s, 1); }
-    mbar_init(req, 1); mbar_init(resp, 4); mbar_init(drain, 1); mbar_init(lsum_ready, 4);
+    mbar_init(req, 1); mbar_init(resp, 4); for (int i = 0; i < kIssuers; ++i) mbar_init(drain + i, 1);
+    mbar_init(lsum_ready, 4);
     for (int s = 0; s < zslots; ++s) { mbar_init(z_full + s, 1); mbar_init(z_empty + s, 4); }
-    for (int s = 0; s < 4; ++s) resc[s] = 0u;
+    for (int s = 0; s < 8; ++s) resc[s] = 0u;       // flags, service lock / phase, issuers_done
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWarpMma) {
@@ -318,117 +352,164 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // z is an input of the whole layer, not a product of the kernels launched just before: the first chunk of every row starts
+  // streaming before the grid-dependency wait (programmatic dependent launch), everything else after it.  The wait is executed
+  // by every thread at a converged point.
+  if (warp == kWarpZ && lane < nvalid && lane < zslots) {
+    const uint32_t bytes = (uint32_t)min(kChunk, N) * kCz * 4;
+    mbar_expect_tx(z_full + lane, bytes);
+    bulk_g2s(ZR + (size_t)lane * kZSlotBytes, z + ((size_t)b * N + i0 + lane) * (size_t)N * kCz, bytes, z_full + lane);
+  }
+  __syncwarp();
+  griddep_wait();
+
   const int wg = warp >> 2;
   if (wg == 0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
-    if (warp == kWarpZ && lane == 0) {
-      // ---------------- z producer (z is an input of the whole layer: it does not wait for the preceding kernels) ----------------
-      const uint8_t* zb = reinterpret_cast<const uint8_t*>(z + ((size_t)b * N + i0) * (size_t)N * kCz);
-      const size_t row_bytes = (size_t)N * kCz * 4;
-      int slot = 0;
-      uint32_t ph = 1;                               // parity of the "empty" phase that precedes the slot's next use
+    if (warp == kWarpZ && lane < nvalid) {
+      // ---------------- z producer: lane r streams query row r (z is an input of the whole layer: no wait for the
+      // preceding kernels).  One lane alone cannot issue 20 bulk copies per chunk fast enough; 20 lanes issue side by side.
+      const uint8_t* zb = reinterpret_cast<const uint8_t*>(z + ((size_t)b * N + i0 + lane) * (size_t)N * kCz);
+      int slot = lane % zslots;                      // item k = chunk * nvalid + row lives in slot k % zslots
+      uint32_t ph = ((uint32_t)(lane / zslots) & 1u) ^ 1u;   // parity of the "empty" phase that precedes the slot's next use
+      RoleProf rp_; rp_.start();
       for (int c = 0; c < nchunks; ++c) {
-        const uint32_t bytes = (uint32_t)min(kChunk, N - c * kChunk) * kCz * 4;
-        for (int r = 0; r < nvalid; ++r) {
-          mbar_wait(z_empty + slot, ph, 101);
+        if (c > 0 || lane >= zslots) {               // chunk 0 was issued before the grid-dependency wait
+          const uint32_t bytes = (uint32_t)min(kChunk, N - c * kChunk) * kCz * 4;
+          rp_.w[0] += mbar_wait(z_empty + slot, ph, 101);
           mbar_expect_tx(z_full + slot, bytes);
-          bulk_g2s(ZR + (size_t)slot * kZSlotBytes, zb + (size_t)r * row_bytes + (size_t)c * kZSlotBytes, bytes, z_full + slot);
-          if (++slot == zslots) { slot = 0; ph ^= 1; }
+          bulk_g2s(ZR + (size_t)slot * kZSlotBytes, zb + (size_t)c * kZSlotBytes, bytes, z_full + slot);
         }
+        slot += nvalid;
+        while (slot >= zslots) { slot -= zslots; ph ^= 1u; }
       }
-    } else if (warp == kWarpKV && lane == 0) {
-      // ---------------- key/value + pair-bias producer ----------------
-      griddep_wait();                                // Qp / KVp come from the kernels launched just before
+      if (lane == 0) rp_.flush(prof, 0);
+    } else if (warp == kWarpZ && lane == 31) {
+      // ---------------- key/value + pair-bias producer (an independently scheduled lane of the same warp) ----------------
+      RoleProf rp_; rp_.start();
       for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1, nk = min(kChunk, N - c * kChunk);
-        mbar_wait(kv_empty + buf, ((c >> 1) & 1) ^ 1, 201);
+        rp_.w[0] += mbar_wait(kv_empty + buf, ((c >> 1) & 1) ^ 1, 201);
         const uint32_t kvb = (uint32_t)nk * kKVRow * 4, bb = (uint32_t)nvalid * kBiasRow * 4;
         mbar_expect_tx(kv_full + buf, kvb + bb);
         bulk_g2s(KVs + (size_t)buf * kChunk * kKVRow, KVp + ((size_t)b * N + c * kChunk) * kKVRow, kvb, kv_full + buf);
         bulk_g2s(BSs + (size_t)buf * kMaxRows * kBiasRow, bias + (((size_t)b * nchunks + c) * N + i0) * kBiasRow, bb, kv_full + buf);
       }
-    } else if (warp == kWarpMma) {
-      // ---------------- MMA issuer ----------------
-      if (lane == 0) {
-        uint32_t dr = 0, rs = 0;
-        int k = 0, aslot = 0;
-        uint32_t aph = 0;
-        for (int c = 0; c < nchunks; ++c) {
-          const int pb = c % kPD;
-          mbar_wait(p_full + pb, (c / kPD) & 1, 301);
+      rp_.flush(prof, 1);
+    } else if (warp >= kWarpMma && warp < kWarpMma + kIssuers) {
+      // ---------------- MMA issuers: warps 1, 2, 3 take the query rows r = 0, 1, 2 (mod 3) ----------------
+      // The whole warp walks the loop (uniform control flow keeps the operand addresses in uniform registers); one elected
+      // lane issues.  Row r is always served by the same warp, so the accumulations into D_r stay ordered.
+      const int mi = warp - kWarpMma;
+      uint64_t* my_drain = drain + mi;
+      uint32_t dr = 0;
+      const uint32_t ptile0 = smem_u32(PT);
+      RoleProf rp_; rp_.start();
+      for (int c = 0; c < nchunks; ++c) {
+        const int pb = c % kPD;
+        rp_.w[0] += mbar_wait(p_full + pb, (c / kPD) & 1, 301);
+        tc_fence_after();
+        const unsigned rm = *reinterpret_cast<volatile unsigned*>(resc + (c & 3));
+        for (int r = mi; r < nvalid; r += kIssuers) {
+          const int k = c * nvalid + r, aslot = k % kASlots;
+          rp_.w[1] += mbar_wait(a_full + aslot, (uint32_t)(k / kASlots) & 1u, 302);
           tc_fence_after();
-          const unsigned rm = *reinterpret_cast<volatile unsigned*>(resc + (c & 3));
-          for (int r = 0; r < nvalid; ++r, ++k) {
-            mbar_wait(a_full + aslot, aph, 302);
-            tc_fence_after();
-            if ((rm >> r) & 1u) {                    // the reference point of some head of row r moved: rescale D_r first
-              umma_commit(drain);
-              mbar_wait(drain, dr, 303); dr ^= 1;
+          if ((rm >> r) & 1u) {                      // the reference point of some head of row r moved: rescale D_r first
+            if (elect_one()) {
+              umma_commit(my_drain);
+              mbar_wait(my_drain, dr, 303);
+              while (atomicCAS(svc_lock, 0u, 1u) != 0u) { }
+              const uint32_t ph = *reinterpret_cast<volatile uint32_t*>(svc_phase);
               req_info[0] = r; req_info[1] = pb;
               mbar_arrive(req);
-              mbar_wait(resp, rs, 304); rs ^= 1;
-              tc_fence_after();
+              mbar_wait(resp, ph & 1u, 304);
+              *reinterpret_cast<volatile uint32_t*>(svc_phase) = ph + 1u;
+              __threadfence_block();
+              atomicExch(svc_lock, 0u);
             }
-            const uint32_t d = tmem_base + 16u * r;
-            const uint32_t a_hi = tmem_base + kACol0 + 16u * aslot, a_lo = a_hi + 8u;
-            const uint64_t b_hi = umma_desc_ptile(smem_u32(PT + (size_t)(pb * kMaxRows + r) * kPTileBytes));
-            const uint64_t b_lo = b_hi + (512 >> 4);
+            dr ^= 1;
+            __syncwarp();
+            tc_fence_after();
+          }
+          const uint32_t d = tmem_base + 16u * r;
+          const uint32_t a_hi = tmem_base + kACol0 + 16u * aslot, a_lo = a_hi + 8u;
+          const uint64_t b_hi = umma_desc_ptile(ptile0 + (uint32_t)(pb * kMaxRows + r) * kPTileBytes);
+          const uint64_t b_lo = b_hi + (512 >> 4);
+          if (elect_one()) {
             umma_tf32_ts(d, a_hi, b_lo, c > 0 ? 1u : 0u);
             umma_tf32_ts(d, a_lo, b_hi, 1u);
             umma_tf32_ts(d, a_hi, b_hi, 1u);
             umma_commit(a_empty + aslot);            // A slot free once these MMAs have read it
-            if (++aslot == kASlots) { aslot = 0; aph ^= 1; }
           }
-          umma_commit(p_empty + pb);                 // probability tiles of the chunk consumed
+          __syncwarp();
         }
-        umma_commit(drain);
-        mbar_wait(drain, dr, 305);
-        req_info[0] = -1; req_info[1] = 0;
-        mbar_arrive(req);
+        if (elect_one()) umma_commit(p_empty + pb);  // this warp's share of the chunk's probability tiles is consumed
+        __syncwarp();
       }
+      if (lane == 0) rp_.flush(prof, 2);
+      if (elect_one()) {
+        umma_commit(my_drain);
+        mbar_wait(my_drain, dr, 305);
+        if (atomicAdd(issuers_done, 1u) == kIssuers - 1) {       // the last issuer tells the service to write the results
+          req_info[0] = -1; req_info[1] = 0;
+          mbar_arrive(req);
+        }
+      }
+      __syncwarp();
     }
   } else if (wg == 1 || wg == 2) {
     // ---------------- converters: z item (8 keys x 128 channels in shared memory) -> A hi / lo in tensor memory ----------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConv));
-    const int cw = wg - 1;                           // this warpgroup converts items cw, cw + 2, ...
+    const int cw = wg - 1;                           // this warpgroup converts the item pairs cw, cw + 2, ... (items 2p, 2p + 1)
     const int q = warp & 3, ch = 32 * q + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + kACol0;
-    int pend = -1;                                   // A slot whose stores are in flight
-    int c = 0, r = cw;
+    // ring positions / phases of the next item, advanced item by item (no runtime divisions in the loop)
+    int k = 2 * cw, c = 0, r = 2 * cw;
     while (r >= nvalid && c < nchunks) { r -= nvalid; ++c; }
-    for (int k = cw; k < nitems; k += 2) {
-      const int zs = k % zslots, as = k % kASlots;
-      const int nk = min(kChunk, N - c * kChunk);
-      mbar_wait(z_full + zs, (uint32_t)(k / zslots) & 1u, 401);
-      const float* zp = reinterpret_cast<const float*>(ZR + (size_t)zs * kZSlotBytes) + ch;
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int kk = 0; kk < kChunk; ++kk) hi[kk] = (kk < nk) ? __float_as_uint(zp[kk * kCz]) : 0u;
-      if (pend >= 0) {                               // previous item: stores done -> hand the slot to the MMA issuer
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full + pend);
-      }
-#pragma unroll
-      for (int kk = 0; kk < kChunk; ++kk)
-        lo[kk] = __float_as_uint(__uint_as_float(hi[kk]) - __uint_as_float(hi[kk] & 0xffffe000u));
-      __syncwarp();                                  // every lane has read the z slot
-      if (lane == 0) mbar_arrive(z_empty + zs);
-      mbar_wait(a_empty + as, ((uint32_t)(k / kASlots) & 1u) ^ 1u, 402);
-      tc_fence_after();
-      tmem_st8(lane_base + 16u * as, hi);
-      tmem_st8(lane_base + 16u * as + 8u, lo);
-      pend = as;
-      r += 2;
+    int zs = k % zslots, as = k % kASlots;
+    uint32_t zph = (uint32_t)(k / zslots) & 1u, aph = ((uint32_t)(k / kASlots) & 1u) ^ 1u;
+    auto advance = [&](int n) {                      // step n items ahead
+      k += n; r += n; zs += n; as += n;
       while (r >= nvalid) { r -= nvalid; ++c; }
-    }
-    if (pend >= 0) {
-      tmem_st_wait();
+      while (zs >= zslots) { zs -= zslots; zph ^= 1u; }
+      while (as >= kASlots) { as -= kASlots; aph ^= 1u; }
+    };
+    RoleProf rp_; rp_.start();
+    while (k < nitems) {
+      // two items per round: the tcgen05.st -> wait::st round trip (and the hand-over to the MMA issuer) is paid once per pair
+      int done[2] = {-1, -1};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (k < nitems) {
+          const int nk = min(kChunk, N - c * kChunk);
+          rp_.w[0] += mbar_wait(z_full + zs, zph, 401);
+          const float* zp = reinterpret_cast<const float*>(ZR + (size_t)zs * kZSlotBytes) + ch;
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int kk = 0; kk < kChunk; ++kk) hi[kk] = (kk < nk) ? __float_as_uint(zp[kk * kCz]) : 0u;
+#pragma unroll
+          for (int kk = 0; kk < kChunk; ++kk)
+            lo[kk] = __float_as_uint(__uint_as_float(hi[kk]) - __uint_as_float(hi[kk] & 0xffffe000u));
+          __syncwarp();                              // every lane has read the z slot
+          if (lane == 0) mbar_arrive(z_empty + zs);
+          rp_.w[1] += mbar_wait(a_empty + as, aph, 402);
+          tc_fence_after();
+          tmem_st8(lane_base + 16u * as, hi);
+          tmem_st8(lane_base + 16u * as + 8u, lo);
+          done[u] = as;
+          advance(u == 0 ? 1 : 3);
+        }
+      }
+      if (done[1] < 0) advance(0);
+      tmem_st_wait();                                // stores done -> hand the slots to the MMA issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + pend);
+      if (lane == 0) {
+        mbar_arrive(a_full + done[0]);
+        if (done[1] >= 0) mbar_arrive(a_full + done[1]);
+      }
     }
+    if (lane == 0) rp_.flush(prof, 3);
   } else if (wg == 3) {
     // ---------------- accumulator service: rescale D_r on request; final normalisation + o_pair store ----------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsSvc));
@@ -436,7 +517,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
     uint32_t ph = 0;
     for (;;) {
-      mbar_wait(req, ph, 501); ph ^= 1;
+      mbar_wait<true>(req, ph, 501); ph ^= 1;
       const int r = req_info[0], pb = req_info[1];
       if (r < 0) break;
       tc_fence_after();
@@ -464,7 +545,6 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   } else if (wg == 4) {
     // ---------------- logits + softmax: thread = (head h, query rows rp and rp + 10), all keys of the chunk ----------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsLogit));
-    griddep_wait();                                  // Qp comes from the kernels launched just before
     const int t = threadIdx.x - kWarpLogit * 32;
     const bool worker = t < kH * kHalfRows;
     const int h = worker ? t / kHalfRows : 0, rp = worker ? t % kHalfRows : 0;
@@ -489,10 +569,11 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     float m0 = -FLT_MAX, m1 = -FLT_MAX, l0 = 0.f, l1 = 0.f;
     const float2 neg1 = make_float2(-1.f, -1.f);
 
+    RoleProf rp_; rp_.start();
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1, pb = c % kPD, j0 = c * kChunk;
-      mbar_wait(kv_full + buf, (c >> 1) & 1, 601);
-      mbar_wait(p_empty + pb, ((c / kPD) & 1) ^ 1, 602);
+      rp_.w[0] += mbar_wait(kv_full + buf, (c >> 1) & 1, 601);
+      rp_.w[1] += mbar_wait(p_empty + pb, ((c / kPD) & 1) ^ 1, 602);
       if (t == 0) resc[(c + 2) & 3] = 0u;
       const float* kvp = KVs + (size_t)buf * kChunk * kKVRow + h * kQK;
       const float* bs0 = BSs + ((size_t)buf * kMaxRows + r0) * kBiasRow + h;
@@ -569,6 +650,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       __syncwarp();
       if (lane == 0) { mbar_arrive(p_full + pb); mbar_arrive(kv_empty + buf); }
     }
+    if (lane == 0) rp_.flush(prof, 4);
     if (act0) LINV[h * kPfRow + pf_row(r0)] = 1.f / l0;
     if (act1) LINV[h * kPfRow + pf_row(r1)] = 1.f / l1;
     __syncwarp();
@@ -586,10 +668,11 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
 #pragma unroll
       for (int d = 0; d < 4; ++d) acc[j][d] = make_float2(0.f, 0.f);
 
+    RoleProf rp_; rp_.start();
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1, pb = c % kPD, nk = min(kChunk, N - c * kChunk);
-      mbar_wait(kv_full + buf, (c >> 1) & 1, 701);
-      mbar_wait(p_full + pb, (c / kPD) & 1, 702);
+      rp_.w[0] += mbar_wait(kv_full + buf, (c >> 1) & 1, 701);
+      rp_.w[1] += mbar_wait(p_full + pb, (c / kPD) & 1, 702);
       {
         const float4* ap = reinterpret_cast<const float4*>(AL + ((size_t)pb * kH + h) * kPfRow + rg * 12);
         const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
@@ -606,7 +689,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       }
       const float* vbase = KVs + (size_t)buf * kChunk * kKVRow + kVOff + h * kVD + 4 * d4;
       const float* pbase = PF + ((size_t)pb * kChunk * kH + h) * kPfRow + rg * 12;
-      for (int kk = 0; kk < nk; ++kk) {
+      auto one_key = [&](int kk) {
         const float4 v = *reinterpret_cast<const float4*>(vbase + kk * kKVRow);
         const float4* pp = reinterpret_cast<const float4*>(pbase + kk * kH * kPfRow);
         const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
@@ -620,11 +703,18 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
           acc[j][2] = ffma2(pr[j], vz, acc[j][2]);
           acc[j][3] = ffma2(pr[j], vw, acc[j][3]);
         }
+      };
+      if (nk == kChunk) {
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) one_key(kk);
+      } else {
+        for (int kk = 0; kk < nk; ++kk) one_key(kk);
       }
       __syncwarp();
       if (lane == 0) { mbar_arrive(p_empty + pb); mbar_arrive(kv_empty + buf); }
     }
 
+    if (lane == 0) rp_.flush(prof, 5);
     // ---- normalise, stage the 480 value outputs of every row, then write o_scalar / o_point / o_point_norm ----
     mbar_wait(lsum_ready, 0, 703);
     asm volatile("bar.sync 1, 256;" ::: "memory");   // every value warp is done with the key/value buffers
@@ -755,6 +845,17 @@ int ipa_watchdog_read(unsigned long long* out) {
   return ABX_OK;
 }
 
+static bool g_prof_on = false;
+// enable != 0: later launches accumulate the per-role stall profile; out64 (optional): copy and clear what was gathered
+int ipa_prof(int enable, unsigned long long* out64) {
+  unsigned long long zero[64] = {0};
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("ipa_prof: %s", cudaGetErrorString(cudaGetLastError())); return ABX_ERR_CUDA; }
+  if (out64) ABX_CUDA(cudaMemcpyFromSymbol(out64, g_ipa_prof, sizeof(zero)));
+  ABX_CUDA(cudaMemcpyToSymbol(g_ipa_prof, zero, sizeof(zero)));
+  g_prof_on = enable != 0;
+  return ABX_OK;
+}
+
 size_t ipa_fused_qp_floats(int B, int N) { return (size_t)B * N * kQRow; }
 size_t ipa_fused_kvp_floats(int B, int N) { return (size_t)B * N * kKVRow; }
 size_t ipa_pair_bias_floats(int B, int N) { return (size_t)B * ceil_div(N, kChunk) * N * kBiasRow; }
@@ -784,8 +885,10 @@ int launch_ipa_fused(cudaStream_t s, int B, int N, const float* Qp, const float*
   const Smem L = smem_layout(N, zslots);
   ABX_REQUIRE(L.total <= 227 * 1024, "ipa_fused: N=%d needs %u bytes of shared memory", N, L.total);
   ABX_CUDA(cudaFuncSetAttribute(ipa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  unsigned long long* prof = nullptr;
+  if (g_prof_on) ABX_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&prof), g_ipa_prof));
   const cudaError_t le = launch_kernel(ipa_fused_kernel, dim3(B * tiles_per_b), dim3(kThreads), (size_t)L.total, s, N, R, tiles_per_b,
-                                       zslots, Qp, KVp, bias, mask, rots, trans, point_weights, z, feats);
+                                       zslots, Qp, KVp, bias, mask, rots, trans, point_weights, z, feats, prof);
   count_launch();
   if (le != cudaSuccess) { set_error("launch of ipa_fused_kernel failed: %s", cudaGetErrorString(le)); return ABX_ERR_CUDA; }
   return check_launch("ipa_fused_kernel");

@@ -56,6 +56,7 @@ SIGNATURES = {
     'abx_ipa_workspace_bytes': (_sz, [_i, _i]),
     'abx_ipa_pair_bias_floats': (_sz, [_i, _i]),
     'abx_ipa_watchdog_read': (_i, [_vp]),
+    'abx_ipa_profile': (_i, [_i, _vp]),
     'abx_ipa_pair_bias': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     'abx_ipa_forward': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(IpaWeights), _vp, _vp, _vp, _vp, _sz]),
     'abx_ipa_attention_features': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(IpaWeights), _vp, _vp, _vp, _sz]),

@@ -252,6 +252,12 @@ int abx_ipa_frame_update(void* stream, int B, int N, const float* upd, const flo
  * out8[0] != 0 means a wait timed out since the last call (the results of that launch are garbage). */
 int abx_ipa_watchdog_read(unsigned long long* out8);
 
+/* Per-role stall profile of the fused attention kernel (development aid; process-wide switch, synchronises the device):
+ * enable != 0 makes later launches add, per role r = 0..5 (z producer, key/value producer, MMA issuers, converters, logits,
+ * values), out64[8 r + 0] = cycles in the role's main loop, [8 r + 1], [8 r + 2] = cycles in its two waits, [8 r + 3] =
+ * contributing warps; out64 (may be NULL) receives and clears what was gathered so far. */
+int abx_ipa_profile(int enable, unsigned long long* out64);
+
 /* Stages of abx_ipa_forward, exported so tests and the benchmark can time/verify them separately. */
 /* feats [B,N,2112] = concat(o_scalar 192, o_point_local (r n) 288, o_point_norm 96, o_pair 1536) */
 int abx_ipa_attention_features(void* stream, int B, int N, const float* x, const float* z, const float* mask,

@@ -20,6 +20,7 @@ def main():
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--precomputed-bias', type=int, default=1)
     ap.add_argument('--profile', type=int, default=0)
+    ap.add_argument('--prof', type=int, default=0, help='per-role stall profile of the fused kernel (abx_ipa_profile) over 5 calls')
     ap.add_argument('--graph', type=int, default=0, help='time G back-to-back layer-calls (same z, as IpaScore issues them) replayed from a CUDA graph')
     a = ap.parse_args()
     from abx_b200.model.folding import InvariantPointAttention
@@ -88,6 +89,23 @@ def main():
             torch.cuda.synchronize()
         for e in sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total)[:10]:
             print(f'{e.self_device_time_total / e.count:9.1f} us x{e.count:3d}  {e.key[:90]}')
+    if a.prof:
+        import ctypes
+        from abx_b200 import lib
+        L = lib.load()
+        lib.check(L.abx_ipa_profile(1, None))
+        with torch.no_grad():
+            for _ in range(5):
+                flush.zero_()
+                ipa(x, z, mask, (rots, trans), pair_bias=bias)
+        buf = (ctypes.c_ulonglong * 64)()
+        lib.check(L.abx_ipa_profile(0, buf))
+        names = ['z producer (wait: slot free)', 'kv producer (wait: buffer free)', 'mma issuers (waits: p_full, a_full)',
+                 'converters (waits: z_full, a_empty)', 'logits (waits: kv_full, p_empty)', 'values (waits: kv_full, p_full)']
+        for r, nm in enumerate(names):
+            loop, w0, w1, n = (buf[8 * r + k] for k in range(4))
+            if n:
+                print(f'  {nm:40s} loop {loop / n / 1.965e3:8.1f} us/call  wait0 {100 * w0 / max(loop, 1):5.1f}%  wait1 {100 * w1 / max(loop, 1):5.1f}%  (n={n})')
     times.sort()
     ms = times[len(times) // 2]
     alg = B * 4 * (128 * N * N + 2 * 256 * N + 12 * N + N) + 4 * 838552

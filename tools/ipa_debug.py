@@ -36,6 +36,16 @@ def main():
         with torch.no_grad():
             feats = ipa.attention_features(x.cuda(), z.cuda(), mask.cuda(), (rots.cuda(), trans.cuda()))
         wd = watchdog()
+        try:
+            with torch.no_grad():
+                bias = ipa.pair_bias(z.cuda())
+                for _ in range(3):
+                    out = ipa(x.cuda(), z.cuda(), mask.cuda(), (rots.cuda(), trans.cuda()), pair_bias=bias)
+                torch.cuda.synchronize()
+            print(f'  forward x3: rel.err {float((out.cpu() - ref).abs().max()) / float(ref.abs().max()):.2e} watchdog={watchdog()[:5]}', flush=True)
+        except Exception as e:
+            print('  forward FAILED:', str(e)[-300:], flush=True)
+            raise
         f, r = feats.cpu(), parts['feats']
         seg = {'o_scalar': (0, 192), 'o_point': (192, 480), 'o_norm': (480, 576), 'o_pair': (576, 2112)}
         line = {k: float((f[..., a:b] - r[..., a:b]).abs().max()) / float(r[..., a:b].abs().max()) for k, (a, b) in seg.items()}
