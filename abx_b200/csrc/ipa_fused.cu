@@ -30,6 +30,7 @@
 // The pair bias sqrt(1/3)(z W^T + b) is read from the chunked key-major tensor written by ipa_pair_bias_kernel
 // ([B, ceil(N/8), N, 100]: row i of chunk c holds bias[j0+k][h] at 12 k + h): one 8 KB bulk copy per chunk and tile.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -62,6 +63,7 @@ static_assert(128 * kRegsCtl + 256 * kRegsConv + 128 * kRegsSvc + 128 * kRegsLog
 constexpr int kFeatPt = kH * kSv, kFeatNorm = kFeatPt + 3 * kH * kPv, kFeatPair = kFeatNorm + kH * kPv;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleGap = 64.f;           // log2 units: the reference point moves when a logit exceeds it by this much
+                                              // (ABX_IPA_RESCALE_GAP overrides it: a small gap makes the rare path the common one in tests)
 
 enum Warps { kWarpZ = 0, kWarpMma = 1, kWarpConv0 = 4, kWarpSvc = 12, kWarpLogit = 16, kWarpVal = 20 };
 
@@ -219,6 +221,19 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Ring ownership.  An mbarrier wait only carries a parity, so a waiter must never reach the wait for use n of a slot before
+// use n-1 has completed: every ring therefore has ONE producer and ONE consumer that walk it in the same order.
+//   * query row r is converted by warpgroup r & 1 and issued by MMA warp r % 3, in every chunk;
+//   * the z ring is split in two (one per converter warpgroup; the producer lane of row r only ever feeds ring r & 1);
+//   * the A ring in tensor memory is split in six two-slot rings, one per (warpgroup, issuer) pair: rows r = rho (mod 6).
+__device__ __forceinline__ int ring_rows(int nvalid, int w, int i) {   // rows of a tile that belong to ring (w, i)
+  const int rho = (3 * w + 4 * i) % 6;                                 // r = rho (mod 6)  <=>  r & 1 == w and r % 3 == i
+  return nvalid > rho ? (nvalid - rho + 5) / 6 : 0;
+}
+// A slot and use count of item (chunk c, row r): slot 2 (3 w + i) + (seq & 1), use seq >> 1
+__device__ __forceinline__ int a_seq(int nvalid, int c, int r) { return c * ring_rows(nvalid, r & 1, r % 3) + r / 6; }
+__device__ __forceinline__ int a_slot(int r, int seq) { return 2 * (3 * (r & 1) + r % 3) + (seq & 1); }
+
 __device__ __forceinline__ int pf_row(int r) { return r + 2 * (r / kHalfRows); }
 
 }  // namespace
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restrict__ Qp, const float* __restrict__ KVp,
                  const float* __restrict__ bias, const float* __restrict__ mask, const float* __restrict__ rots,
                  const float* __restrict__ trans, const float* __restrict__ point_weights, const float* __restrict__ z,
-                 float* __restrict__ feats, unsigned long long* __restrict__ prof) {
+                 float* __restrict__ feats, unsigned long long* __restrict__ prof, float rescale_gap) {
   // no swizzled operand tiles here: 16-byte alignment (bulk copies, descriptors) is all the carve-up needs, so the dynamic
   // shared array is used as is and every access below stays a shared-state-space instruction (LDS / STS)
   extern __shared__ __align__(128) uint8_t sm[];
@@ -295,7 +310,6 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   const int b = blockIdx.x / tiles_per_b, i0 = (blockIdx.x % tiles_per_b) * R;
   const int nvalid = min(R, N - i0);                // query rows of this tile
   const int nchunks = (N + kChunk - 1) / kChunk;
-  const int nitems = nchunks * nvalid;              // item k = chunk * nvalid + row
 
   float* KVs = reinterpret_cast<float*>(sm + L.kv);           // [2][8][816]
   float* BSs = reinterpret_cast<float*>(sm + L.bias);         // [2][R][100]
@@ -355,10 +369,12 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   // z is an input of the whole layer, not a product of the kernels launched just before: the first chunk of every row starts
   // streaming before the grid-dependency wait (programmatic dependent launch), everything else after it.  The wait is executed
   // by every thread at a converged point.
-  if (warp == kWarpZ && lane < nvalid && lane < zslots) {
+  const int zring0 = (zslots + 1) / 2;             // z ring of warpgroup 0: slots [0, zring0); warpgroup 1: [zring0, zslots)
+  if (warp == kWarpZ && lane < nvalid) {
+    const int slot = (lane & 1) * zring0 + (lane >> 1);
     const uint32_t bytes = (uint32_t)min(kChunk, N) * kCz * 4;
-    mbar_expect_tx(z_full + lane, bytes);
-    bulk_g2s(ZR + (size_t)lane * kZSlotBytes, z + ((size_t)b * N + i0 + lane) * (size_t)N * kCz, bytes, z_full + lane);
+    mbar_expect_tx(z_full + slot, bytes);
+    bulk_g2s(ZR + (size_t)slot * kZSlotBytes, z + ((size_t)b * N + i0 + lane) * (size_t)N * kCz, bytes, z_full + slot);
   }
   __syncwarp();
   griddep_wait();
@@ -370,18 +386,21 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       // ---------------- z producer: lane r streams query row r (z is an input of the whole layer: no wait for the
       // preceding kernels).  One lane alone cannot issue 20 bulk copies per chunk fast enough; 20 lanes issue side by side.
       const uint8_t* zb = reinterpret_cast<const uint8_t*>(z + ((size_t)b * N + i0 + lane) * (size_t)N * kCz);
-      int slot = lane % zslots;                      // item k = chunk * nvalid + row lives in slot k % zslots
-      uint32_t ph = ((uint32_t)(lane / zslots) & 1u) ^ 1u;   // parity of the "empty" phase that precedes the slot's next use
+      const int w = lane & 1, zbase = w * zring0, zn = w ? zslots - zring0 : zring0;   // this row's ring
+      const int nw = (nvalid + 1 - w) >> 1;          // rows of the tile in that ring = ring positions per chunk (<= zn)
+      int pos = lane >> 1;                           // ring position of (chunk c, this row), modulo zn
+      uint32_t ph = 1u;                              // parity of the "empty" phase that precedes the slot's next use
       RoleProf rp_; rp_.start();
       for (int c = 0; c < nchunks; ++c) {
-        if (c > 0 || lane >= zslots) {               // chunk 0 was issued before the grid-dependency wait
+        if (c > 0) {                                 // chunk 0 was issued before the grid-dependency wait
           const uint32_t bytes = (uint32_t)min(kChunk, N - c * kChunk) * kCz * 4;
+          const int slot = zbase + pos;
           rp_.w[0] += mbar_wait(z_empty + slot, ph, 101);
           mbar_expect_tx(z_full + slot, bytes);
           bulk_g2s(ZR + (size_t)slot * kZSlotBytes, zb + (size_t)c * kZSlotBytes, bytes, z_full + slot);
         }
-        slot += nvalid;
-        while (slot >= zslots) { slot -= zslots; ph ^= 1u; }
+        pos += nw;
+        if (pos >= zn) { pos -= zn; ph ^= 1u; }
       }
       if (lane == 0) rp_.flush(prof, 0);
     } else if (warp == kWarpZ && lane == 31) {
@@ -411,8 +430,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
         tc_fence_after();
         const unsigned rm = *reinterpret_cast<volatile unsigned*>(resc + (c & 3));
         for (int r = mi; r < nvalid; r += kIssuers) {
-          const int k = c * nvalid + r, aslot = k % kASlots;
-          rp_.w[1] += mbar_wait(a_full + aslot, (uint32_t)(k / kASlots) & 1u, 302);
+          const int seq = a_seq(nvalid, c, r), aslot = a_slot(r, seq);
+          rp_.w[1] += mbar_wait(a_full + aslot, (uint32_t)(seq >> 1) & 1u, 302);
           tc_fence_after();
           if ((rm >> r) & 1u) {                      // the reference point of some head of row r moved: rescale D_r first
             if (elect_one()) {
@@ -460,28 +479,26 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   } else if (wg == 1 || wg == 2) {
     // ---------------- converters: z item (8 keys x 128 channels in shared memory) -> A hi / lo in tensor memory ----------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConv));
-    const int cw = wg - 1;                           // this warpgroup converts the item pairs cw, cw + 2, ... (items 2p, 2p + 1)
+    const int cw = wg - 1;                           // this warpgroup converts the query rows r = cw (mod 2), in chunk order
     const int q = warp & 3, ch = 32 * q + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + kACol0;
-    // ring positions / phases of the next item, advanced item by item (no runtime divisions in the loop)
-    int k = 2 * cw, c = 0, r = 2 * cw;
-    while (r >= nvalid && c < nchunks) { r -= nvalid; ++c; }
-    int zs = k % zslots, as = k % kASlots;
-    uint32_t zph = (uint32_t)(k / zslots) & 1u, aph = ((uint32_t)(k / kASlots) & 1u) ^ 1u;
-    auto advance = [&](int n) {                      // step n items ahead
-      k += n; r += n; zs += n; as += n;
-      while (r >= nvalid) { r -= nvalid; ++c; }
-      while (zs >= zslots) { zs -= zslots; zph ^= 1u; }
-      while (as >= kASlots) { as -= kASlots; aph ^= 1u; }
+    const int zbase = cw * zring0, zn = cw ? zslots - zring0 : zring0;
+    int c = 0, r = cw, zpos = 0;                     // next item (chunk, row) and its z ring position
+    uint32_t zph = 0u;
+    auto advance = [&]() {
+      r += 2;
+      if (r >= nvalid) { r = cw; ++c; }
+      if (++zpos == zn) { zpos = 0; zph ^= 1u; }
     };
     RoleProf rp_; rp_.start();
-    while (k < nitems) {
-      // two items per round: the tcgen05.st -> wait::st round trip (and the hand-over to the MMA issuer) is paid once per pair
+    while (c < nchunks && r < nvalid) {
+      // two items per round: the tcgen05.st -> wait::st round trip (and the hand-over to the MMA issuers) is paid once per pair
       int done[2] = {-1, -1};
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        if (k < nitems) {
+        if (c < nchunks) {
           const int nk = min(kChunk, N - c * kChunk);
+          const int zs = zbase + zpos;
           rp_.w[0] += mbar_wait(z_full + zs, zph, 401);
           const float* zp = reinterpret_cast<const float*>(ZR + (size_t)zs * kZSlotBytes) + ch;
           uint32_t hi[8], lo[8];
@@ -492,16 +509,16 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
             lo[kk] = __float_as_uint(__uint_as_float(hi[kk]) - __uint_as_float(hi[kk] & 0xffffe000u));
           __syncwarp();                              // every lane has read the z slot
           if (lane == 0) mbar_arrive(z_empty + zs);
-          rp_.w[1] += mbar_wait(a_empty + as, aph, 402);
+          const int seq = a_seq(nvalid, c, r), as = a_slot(r, seq);
+          rp_.w[1] += mbar_wait(a_empty + as, ((uint32_t)(seq >> 1) & 1u) ^ 1u, 402);
           tc_fence_after();
           tmem_st8(lane_base + 16u * as, hi);
           tmem_st8(lane_base + 16u * as + 8u, lo);
           done[u] = as;
-          advance(u == 0 ? 1 : 3);
+          advance();
         }
       }
-      if (done[1] < 0) advance(0);
-      tmem_st_wait();                                // stores done -> hand the slots to the MMA issuer
+      tmem_st_wait();                                // stores done -> hand the slots to the MMA issuers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -520,13 +537,20 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       mbar_wait<true>(req, ph, 501); ph ^= 1;
       const int r = req_info[0], pb = req_info[1];
       if (r < 0) break;
+      if (threadIdx.x == kWarpSvc * 32) atomicAdd(&g_ipa_watchdog[6], 1ull);     // statistics: rescale requests served
       tc_fence_after();
       uint32_t v[16];
       tmem_ld16(lane_base + 16u * r, v);
       const float* al = AL + (size_t)pb * kH * kPfRow + pf_row(r);
 #pragma unroll
       for (int h = 0; h < kH; ++h) v[h] = __float_as_uint(__uint_as_float(v[h]) * al[h * kPfRow]);
-      tmem_st16(lane_base + 16u * r, v);
+      {
+        uint32_t lo8[8], hi8[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) { lo8[h] = v[h]; hi8[h] = v[8 + h]; }
+        tmem_st8(lane_base + 16u * r, lo8);
+        tmem_st8(lane_base + 16u * r + 8u, hi8);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -616,7 +640,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
         float alpha = 1.f;
         if (c == 0) {
           m = cm;
-        } else if (cm > m + kRescaleGap) {           // move the reference point: accumulators are scaled by alpha
+        } else if (cm > m + rescale_gap) {           // move the reference point: accumulators are scaled by alpha
           alpha = exp2f(m - cm);
           m = cm;
           l *= alpha;
@@ -816,6 +840,8 @@ __global__ void __launch_bounds__(256) ipa_pair_bias_chunked_kernel(int N, const
 // Tile height: time ~ rounds * (R + 6.4) — R rows of z per tile plus the tile's key / value chunks (3264 B per key
 // against 512 B of z per key and row), rounds = ceil(tiles / SMs).
 static int choose_rows(int B, int N, int sms) {
+  static int forced = [] { const char* e = getenv("ABX_IPA_ROWS"); return e ? atoi(e) : 0; }();   // test knob: fixed tile height
+  if (forced >= 1 && forced <= kMaxRows) return forced < N ? forced : N;
   int best = 1;
   double best_cost = 1e30;
   for (int R = 1; R <= kMaxRows && R <= N; ++R) {
@@ -843,6 +869,11 @@ int ipa_watchdog_read(unsigned long long* out) {
   ABX_CUDA(cudaMemcpyFromSymbol(out, g_ipa_watchdog, sizeof(zero)));
   ABX_CUDA(cudaMemcpyToSymbol(g_ipa_watchdog, zero, sizeof(zero)));
   return ABX_OK;
+}
+
+static float rescale_gap() {
+  static float v = [] { const char* e = getenv("ABX_IPA_RESCALE_GAP"); return e ? (float)atof(e) : kRescaleGap; }();
+  return v;
 }
 
 static bool g_prof_on = false;
@@ -884,11 +915,12 @@ int launch_ipa_fused(cudaStream_t s, int B, int N, const float* Qp, const float*
   while (zslots > 4 && smem_layout(N, zslots).total > 227 * 1024) --zslots;
   const Smem L = smem_layout(N, zslots);
   ABX_REQUIRE(L.total <= 227 * 1024, "ipa_fused: N=%d needs %u bytes of shared memory", N, L.total);
+  ABX_REQUIRE(zslots / 2 >= (R + 1) / 2, "ipa_fused: N=%d leaves %d z slots, too few for %d-row tiles", N, zslots, R);
   ABX_CUDA(cudaFuncSetAttribute(ipa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   unsigned long long* prof = nullptr;
   if (g_prof_on) ABX_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&prof), g_ipa_prof));
   const cudaError_t le = launch_kernel(ipa_fused_kernel, dim3(B * tiles_per_b), dim3(kThreads), (size_t)L.total, s, N, R, tiles_per_b,
-                                       zslots, Qp, KVp, bias, mask, rots, trans, point_weights, z, feats, prof);
+                                       zslots, Qp, KVp, bias, mask, rots, trans, point_weights, z, feats, prof, rescale_gap());
   count_launch();
   if (le != cudaSuccess) { set_error("launch of ipa_fused_kernel failed: %s", cudaGetErrorString(le)); return ABX_ERR_CUDA; }
   return check_launch("ipa_fused_kernel");

@@ -104,6 +104,22 @@ def test_ipa_reference_point_moves(cuda_device, B, N):
     assert maxabs(out.cpu(), ref) < 3e-5 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize('rows,sizes', [(20, '2,350'), (17, '1,350'), (7, '3,100')])
+def test_ipa_rescale_path_at_every_tile_height(cuda_device, rows, sizes):
+    """The rare path made the common one: ABX_IPA_RESCALE_GAP=1 moves the softmax reference points (and rescales the
+    tensor-memory accumulators through the service warps) in almost every chunk, ABX_IPA_ROWS fixes the tile height (full
+    20-row tiles use all three MMA issuers, both converter warpgroups, every A ring and accumulator columns >= 256).
+    tools/ipa_debug.py compares features and layer output with the oracle (3e-5) and reads the kernel's watchdog."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {**os.environ, 'ABX_IPA_RESCALE_GAP': '1.0', 'ABX_IPA_ROWS': str(rows)}
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'ipa_debug.py'), sizes], env=env, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_ipa_is_frame_invariant(cuda_device):
     """Size-independent property at full size: a global rigid motion of all frames leaves the output unchanged."""
     ipa, _ = make_ipa()

@@ -23,6 +23,7 @@ def watchdog():
 def main():
     sizes = [tuple(int(v) for v in a.split(',')) for a in sys.argv[1:]] or [(2, 37)]
     ipa, P = make_ipa()
+    failed = []
     for B, N in sizes:
         gen = torch.Generator().manual_seed(100 + N)
         x, z = np_randn(300 + N, B, N, 256), np_randn(400 + N, B, N, N, 128)
@@ -50,12 +51,17 @@ def main():
         seg = {'o_scalar': (0, 192), 'o_point': (192, 480), 'o_norm': (480, 576), 'o_pair': (576, 2112)}
         line = {k: float((f[..., a:b] - r[..., a:b]).abs().max()) / float(r[..., a:b].abs().max()) for k, (a, b) in seg.items()}
         print(f'B={B} N={N} watchdog={wd[:5]} rel.err={line} finite={bool(torch.isfinite(f).all())}', flush=True)
+        if wd[0] != 0 or not max(line.values()) < 3e-5:
+            failed.append((B, N))
         if wd[0] == 0 and max(line.values()) > 1e-3:
             d = (f - r).abs()
             bad = torch.nonzero(d > 1e-3 * r.abs().max())
             print('  first bad entries (b, i, col):', bad[:8].tolist(), ' of', len(bad))
             b0, i0, c0 = bad[0].tolist()
             print('  got', f[b0, i0, c0:c0 + 4].tolist(), 'want', r[b0, i0, c0:c0 + 4].tolist())
+    if failed:
+        print('FAILED:', failed)
+        sys.exit(1)
 
 
 if __name__ == '__main__':
