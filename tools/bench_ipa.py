@@ -104,6 +104,8 @@ def main():
                  'converters (waits: z_full, a_empty)', 'logits (waits: kv_full, p_empty)', 'values (waits: kv_full, p_full)']
         for r, nm in enumerate(names):
             loop, w0, w1, n = (buf[8 * r + k] for k in range(4))
+            if n and (buf[8 * r + 4] or buf[8 * r + 5]):
+                print(f'      extra: t2 {100 * buf[8 * r + 4] / max(loop, 1):5.1f}%  t3 {100 * buf[8 * r + 5] / max(loop, 1):5.1f}% of the loop')
             if n:
                 print(f'  {nm:40s} loop {loop / n / 1.965e3:8.1f} us/call  wait0 {100 * w0 / max(loop, 1):5.1f}%  wait1 {100 * w1 / max(loop, 1):5.1f}%  (n={n})')
     times.sort()

@@ -1,7 +1,5 @@
+bash tools/gpu_quick_ipa.sh q24 2>&1 | grep "B=\|loop\|ipa_fused_kernel\|ms_per_layer\|FAILED\|rror" | cut -c1-220
 export ABX_IPA_RESCALE_GAP=1.0
-for R in 17 20; do echo "--- debug 2,350 gap 1 R=$R"; ABX_IPA_ROWS=$R timeout 150 python tools/ipa_debug.py 2,350 2>&1 | grep -v Warning | tail -2 | cut -c1-300; done
+for R in 20; do echo "--- debug 2,350 gap 1 R=$R"; ABX_IPA_ROWS=$R timeout 150 python tools/ipa_debug.py 2,350 2>&1 | grep -v Warning | tail -2 | cut -c1-200; done
 unset ABX_IPA_RESCALE_GAP
-run() { echo "--- stress $*"; timeout 150 python tools/ipa_stress.py $* 2>&1 | grep -v "Warning\|^$\|Search for\|might be\|For debugging\|Compile with\|File \|\^\^\^" | tail -3; }
-run 8 350 16 2.0 0.1
-run 8 350 8 8.0 0.1
-echo "--- sizes"; timeout 150 python tools/ipa_debug.py 1,1 1,7 2,37 5,131 2>&1 | grep -v Warning | grep "B=" | cut -c1-120
+echo "--- stress"; timeout 150 python tools/ipa_stress.py 8 350 6 8.0 0.1 2>&1 | grep -v "Warning\|^$" | tail -2
