@@ -54,14 +54,16 @@ constexpr int kBiasRow = ABX_IPA_BIAS_ROW;    // floats per (chunk, row) of the 
 constexpr int kPD = 2;                        // chunks of probabilities in flight
 constexpr int kPTileBytes = 1040;             // per item: hi tile 512 B | lo tile 512 B | 16 B stagger (bank spread)
 constexpr int kPfRow = 24;                    // plain probabilities pf[key][head][24]: row r at r + 2 (r / 10)
-constexpr int kASlots = 12, kACol0 = kMaxRows * 16;   // tensor memory: D_i at columns 16 i, A ring at 320 + 16 slot
+constexpr int kASlots = 12, kACol0 = kMaxRows * 16;   // tensor memory: D_i at columns 16 i, A rings (3 x 4 slots) at 320 + 16 slot
 constexpr uint32_t kTmemCols = 512;
 constexpr int kZSlotBytes = kChunk * kCz * 4; // 4096
 constexpr int kKVChunkBytes = kChunk * kKVRow * 4;    // 26112
+constexpr int kCols = 3;                      // "columns": query row r is converted by warpgroup r % 3 and issued by MMA warp r % 3
 constexpr int kThreads = 896;
-constexpr int kIssuers = 3;                   // MMA issuer warps (query rows interleaved)
-constexpr int kRegsCtl = 48, kRegsConv = 48, kRegsSvc = 40, kRegsLogit = 128, kRegsVal = 96;   // 64512 of 65536
-static_assert(128 * kRegsCtl + 256 * kRegsConv + 128 * kRegsSvc + 128 * kRegsLogit + 256 * kRegsVal <= 65536, "register budget");
+constexpr int kValThreads = 128;
+constexpr int kIssuers = kCols;               // MMA issuer warps
+constexpr int kRegsCtl = 48, kRegsConv = 48, kRegsSvc = 40, kRegsLogit = 128, kRegsVal = 128;   // 62464 of 65536
+static_assert(128 * kRegsCtl + 384 * kRegsConv + 128 * kRegsSvc + 128 * kRegsLogit + 128 * kRegsVal <= 65536, "register budget");
 constexpr int kFeatPt = kH * kSv, kFeatNorm = kFeatPt + 3 * kH * kPv, kFeatPair = kFeatNorm + kH * kPv;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleGap = 64.f;           // log2 units: the reference point moves when a logit exceeds it by this much
@@ -69,7 +71,7 @@ constexpr float kRescaleGap = 64.f;           // log2 units: the reference point
 
 // Warp ids are priorities: among the eligible warps of a scheduler the highest id issues first.  The latency-critical roles
 // (converters, MMA issuers, producers) therefore sit above the FFMA2-dense logit / value warps, which have slack.
-enum Warps { kWarpVal = 0, kWarpLogit = 8, kWarpSvc = 12, kWarpZ = 16, kWarpMma = 17, kWarpConv0 = 20 };
+enum Warps { kWarpVal = 0, kWarpLogit = 4, kWarpSvc = 8, kWarpZ = 12, kWarpMma = 13, kWarpConv0 = 16 };
 enum WarpGroups { kWgLogit = kWarpLogit / 4, kWgSvc = kWarpSvc / 4, kWgCtl = kWarpZ / 4, kWgConv0 = kWarpConv0 / 4 };
 
 // ---- shared-memory carve-up (byte offsets from a 128-byte aligned base) ----
@@ -232,17 +234,12 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // Ring ownership.  An mbarrier wait only carries a parity, so a waiter must never reach the wait for use n of a slot before
-// use n-1 has completed: every ring therefore has ONE producer and ONE consumer that walk it in the same order.
-//   * query row r is converted by warpgroup r & 1 and issued by MMA warp r % 3, in every chunk;
-//   * the z ring is split in two (one per converter warpgroup; the producer lane of row r only ever feeds ring r & 1);
-//   * the A ring in tensor memory is split in six two-slot rings, one per (warpgroup, issuer) pair: rows r = rho (mod 6).
-__device__ __forceinline__ int ring_rows(int nvalid, int w, int i) {   // rows of a tile that belong to ring (w, i)
-  const int rho = (3 * w + 4 * i) % 6;                                 // r = rho (mod 6)  <=>  r & 1 == w and r % 3 == i
-  return nvalid > rho ? (nvalid - rho + 5) / 6 : 0;
-}
-// A slot and use count of item (chunk c, row r): slot 2 (3 w + i) + (seq & 1), use seq >> 1
-__device__ __forceinline__ int a_seq(int nvalid, int c, int r) { return c * ring_rows(nvalid, r & 1, r % 3) + r / 6; }
-__device__ __forceinline__ int a_slot(int r, int seq) { return 2 * (3 * (r & 1) + r % 3) + (seq & 1); }
+// use n-1 has completed: every ring therefore has ONE producer and ONE consumer that walk it in the same order.  Query row r
+// belongs to "column" r % 3 in every chunk: it is streamed into z ring r % 3 by producer lane r, converted by converter
+// warpgroup r % 3 into A ring r % 3 (4 tensor-memory slots) and issued by MMA warp r % 3.
+__device__ __forceinline__ int col_rows(int nvalid, int j) { return nvalid > j ? (nvalid - j + kCols - 1) / kCols : 0; }
+__device__ __forceinline__ int zring_base(int zslots, int j) { return j * (zslots / kCols) + min(j, zslots % kCols); }
+__device__ __forceinline__ int zring_size(int zslots, int j) { return zslots / kCols + (j < zslots % kCols ? 1 : 0); }
 
 __device__ __forceinline__ int pf_row(int r) { return r + 2 * (r / kHalfRows); }
 
@@ -339,9 +336,9 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   uint8_t* ZR = sm + L.zring;                                  // [zslots][4096]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
   uint64_t* kv_full = bars;                         // [2]
-  uint64_t* kv_empty = bars + 2;                    // [2]  4 logit warps + 8 value warps
+  uint64_t* kv_empty = bars + 2;                    // [2]  4 logit warps + 4 value warps
   uint64_t* p_full = bars + 4;                      // [kPD] 4 logit warps
-  uint64_t* p_empty = bars + 6;                     // [kPD] MMA issuers' commits + 8 value warps
+  uint64_t* p_empty = bars + 6;                     // [kPD] MMA issuers' commits + 4 value warps
   uint64_t* a_full = bars + 8;                      // [12] 4 converter warps
   uint64_t* a_empty = bars + 20;                    // [12] MMA commit
   uint64_t* req = bars + 32;                        // MMA -> accumulator service
@@ -358,8 +355,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resc + 8);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 12); }
-    for (int s = 0; s < kPD; ++s) { mbar_init(p_full + s, 4); mbar_init(p_empty + s, 8 + kIssuers); }
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 4 + kValThreads / 32); }
+    for (int s = 0; s < kPD; ++s) { mbar_init(p_full + s, 4); mbar_init(p_empty + s, kValThreads / 32 + kIssuers); }
     for (int s = 0; s < kASlots; ++s) { mbar_init(a_full + s, 4); mbar_init(a_empty + s, 1); }
     mbar_init(req, 1); mbar_init(resp, 4); for (int i = 0; i < kIssuers; ++i) mbar_init(drain + i, 1);
     mbar_init(lsum_ready, 4);
@@ -387,9 +384,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   // z is an input of the whole layer, not a product of the kernels launched just before: the first chunk of every row starts
   // streaming before the grid-dependency wait (programmatic dependent launch), everything else after it.  The wait is executed
   // by every thread at a converged point.
-  const int zring0 = (zslots + 1) / 2;             // z ring of warpgroup 0: slots [0, zring0); warpgroup 1: [zring0, zslots)
   if (warp == kWarpZ && lane < nvalid) {
-    const int slot = (lane & 1) * zring0 + (lane >> 1);
+    const int slot = zring_base(zslots, lane % kCols) + lane / kCols;
     const uint32_t bytes = (uint32_t)min(kChunk, N) * kCz * 4;
     mbar_expect_tx(z_full + slot, bytes);
     bulk_g2s(ZR + (size_t)slot * kZSlotBytes, z + ((size_t)b * N + i0 + lane) * (size_t)N * kCz, bytes, z_full + slot);
@@ -404,9 +400,9 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       // ---------------- z producer: lane r streams query row r (z is an input of the whole layer: no wait for the
       // preceding kernels).  One lane alone cannot issue 20 bulk copies per chunk fast enough; 20 lanes issue side by side.
       const uint8_t* zb = reinterpret_cast<const uint8_t*>(z + ((size_t)b * N + i0 + lane) * (size_t)N * kCz);
-      const int w = lane & 1, zbase = w * zring0, zn = w ? zslots - zring0 : zring0;   // this row's ring
-      const int nw = (nvalid + 1 - w) >> 1;          // rows of the tile in that ring = ring positions per chunk (<= zn)
-      int pos = lane >> 1;                           // ring position of (chunk c, this row), modulo zn
+      const int col = lane % kCols, zbase = zring_base(zslots, col), zn = zring_size(zslots, col);   // this row's ring
+      const int nw = col_rows(nvalid, col);          // rows of the tile in that ring = ring positions per chunk (<= zn)
+      int pos = lane / kCols;                        // ring position of (chunk c, this row), modulo zn
       uint32_t ph = 1u;                              // parity of the "empty" phase that precedes the slot's next use
       RoleProf rp_; if constexpr (kProf) rp_.start();
       for (int c = 0; c < nchunks; ++c) {
@@ -442,9 +438,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       const uint32_t ptile0 = smem_u32(PT);
       RoleProf rp_; if constexpr (kProf) rp_.start();
       const int mi = warp - kWarpMma;
-      const int nr_even = ring_rows(nvalid, 0, mi), nr_odd = ring_rows(nvalid, 1, mi);
       const unsigned my_rows = 0x249249u << mi;      // bits r = mi (mod 3)
-      int base_even = 0, base_odd = 0;               // chunk * rows of the ring = use count of the ring at the chunk's start
+      int seq = 0;                                   // items issued so far = position in A ring mi
       for (int c = 0; c < nchunks; ++c) {
         const int pb = c % kPD;
         ABX_WAIT(0, p_full + pb, (c / kPD) & 1, 301);
@@ -474,10 +469,9 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
           tc_fence_after();
         }
         const uint32_t pt = ptile0 + (uint32_t)(pb * kMaxRows) * kPTileBytes;
-        for (int r = mi; r < nvalid; r += kIssuers) {
-          const int w = r & 1, seq = (w ? base_odd : base_even) + ((r * 43) >> 8);     // r / 6 for r < 64
-          const int aslot = 2 * (3 * w + mi) + (seq & 1);
-          ABX_WAIT(1, a_full + aslot, (uint32_t)(seq >> 1) & 1u, 302);
+        for (int r = mi; r < nvalid; r += kIssuers, ++seq) {
+          const int aslot = 4 * mi + (seq & 3);
+          ABX_WAIT(1, a_full + aslot, (uint32_t)(seq >> 2) & 1u, 302);
           tc_fence_after();
           const uint32_t d = tmem_base + 16u * r;
           const uint32_t a_hi = tmem_base + kACol0 + 16u * aslot, a_lo = a_hi + 8u;
@@ -491,7 +485,6 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
           }
         }
         if (elect_one()) umma_commit(p_empty + pb);  // this warp's share of the chunk's probability tiles is consumed
-        base_even += nr_even; base_odd += nr_odd;
       }
       __syncwarp();
       if constexpr (kProf) { if (lane == 0) rp_.flush(prof, 2); }
@@ -508,20 +501,22 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   } else if (wg >= kWgConv0) {
     // ---------------- converters: z item (8 keys x 128 channels in shared memory) -> A hi / lo in tensor memory ----------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConv));
-    const int cw = wg - kWgConv0;                           // this warpgroup converts the query rows r = cw (mod 2), in chunk order
+    const int cw = wg - kWgConv0;                    // this warpgroup converts the query rows r = cw (mod 3), in chunk order
     const int q = warp & 3, ch = 32 * q + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + kACol0;
-    const int zbase = cw * zring0, zn = cw ? zslots - zring0 : zring0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + kACol0 + 64u * cw;   // A ring cw: 4 slots of 16 columns
+    const int zbase = zring_base(zslots, cw), zn = zring_size(zslots, cw);
     RoleProf rp_; if constexpr (kProf) rp_.start();
-    // Two items per round, every stage for both at once: one shared-memory round trip, one tcgen05.st -> wait::st round trip
-    // and one hand-over to the MMA issuers per pair.
+    // Two items per round, every stage for both at once: one shared-memory round trip and one hand-over to the MMA issuer per
+    // pair; the hand-over of a round (tcgen05.wait::st + arrive) is done while the next round's loads are in flight.
     {
-      const int w = cw;
-      const int nr0 = ring_rows(nvalid, w, 0), nr1 = ring_rows(nvalid, w, 1), nr2 = ring_rows(nvalid, w, 2);
-      int base0 = 0, base1 = 0, base2 = 0;           // use counts of the three A rings at the chunk's start
+      int seq = 0;                                   // items converted so far = position in A ring cw
       int zpos = 0;
       uint32_t zph = 0u;
       const uint32_t zr0 = smem_u32(ZR) + (uint32_t)zbase * kZSlotBytes + (uint32_t)ch * 4u;
+      uint64_t* const zf = z_full + zbase;
+      uint64_t* const ze = z_empty + zbase;
+      uint64_t* const af = a_full + 4 * cw;
+      uint64_t* const ae = a_empty + 4 * cw;
       auto load_item = [&](int zs, int nk, uint32_t (&hi)[16]) {
         const uint32_t addr = zr0 + (uint32_t)zs * kZSlotBytes;
 #pragma unroll
@@ -535,33 +530,25 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
 #pragma unroll
         for (int kk = 0; kk < kChunk; ++kk) v[8 + kk] = __float_as_uint(__uint_as_float(v[kk]) - __uint_as_float(v[kk] & 0xffffe000u));
       };
-      auto a_slot_of = [&](int r, int& as, uint32_t& ap) {         // A ring slot of row r in the current chunk + its "empty" parity
-        const int i3 = r % 3, seq = (i3 == 0 ? base0 : (i3 == 1 ? base1 : base2)) + ((r * 43) >> 8);
-        as = 2 * (3 * w + i3) + (seq & 1);
-        ap = ((uint32_t)(seq >> 1) & 1u) ^ 1u;
-      };
       int pendA = -1, pendB = -1;                    // A slots whose stores are in flight (signalled one round later)
-      auto hand_over = [&]() {                       // previous round: stores done -> hand the slots to the MMA issuers
+      auto hand_over = [&]() {                       // previous round: stores done -> hand the slots to the MMA issuer
         if (pendA >= 0) {
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(a_full + pendA);
-            if (pendB >= 0) mbar_arrive(a_full + pendB);
+            mbar_arrive(af + pendA);
+            if (pendB >= 0) mbar_arrive(af + pendB);
           }
         }
       };
       for (int c = 0; c < nchunks; ++c) {
         const int nk = min(kChunk, N - c * kChunk);
-        for (int rA = w; rA < nvalid; rA += 4) {
-          unsigned tq0 = 0u, tq1 = 0u;
-          if constexpr (kProf) tq0 = (unsigned)clock64();
-          const bool two = rA + 2 < nvalid;
-          int asA, asB = -1;
-          uint32_t apA, apB = 0u;
-          a_slot_of(rA, asA, apA);
-          if (two) a_slot_of(rA + 2, asB, apB);
+        for (int rA = cw; rA < nvalid; rA += 2 * kCols) {
+          const bool two = rA + kCols < nvalid;
+          const int asA = seq & 3, asB = two ? ((seq + 1) & 3) : -1;
+          const uint32_t apA = ((uint32_t)(seq >> 2) & 1u) ^ 1u, apB = ((uint32_t)((seq + 1) >> 2) & 1u) ^ 1u;
+          seq += two ? 2 : 1;
           const int zsA = zpos;
           const uint32_t zpA = zph;
           if (++zpos == zn) { zpos = 0; zph ^= 1u; }
@@ -569,31 +556,27 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
           const uint32_t zpB = zph;
           if (two) { if (++zpos == zn) { zpos = 0; zph ^= 1u; } }
           uint32_t vA[16], vB[16];                  // [0, 8): hi = the raw words, [8, 16): lo — one 16-column tcgen05.st per item
-          if constexpr (kProf) rp_.w[2] += (unsigned)clock64() - tq0;
-          ABX_WAIT(0, z_full + zbase + zsA, zpA, 401);
+          ABX_WAIT(0, zf + zsA, zpA, 401);
           load_item(zsA, nk, vA);
           if (two) {
-            ABX_WAIT(0, z_full + zbase + zsB, zpB, 401);
+            ABX_WAIT(0, zf + zsB, zpB, 401);
             load_item(zsB, nk, vB);
           }
-          if constexpr (kProf) tq1 = (unsigned)clock64();
           hand_over();                               // overlaps the shared-memory round trip of this round's loads
-          if constexpr (kProf) rp_.w[3] += (unsigned)clock64() - tq1;
           low_part(vA);
           if (two) low_part(vB);
           __syncwarp();                              // every lane has read (and used) the z slots
           if (lane == 0) {
-            mbar_arrive(z_empty + zbase + zsA);
-            if (two) mbar_arrive(z_empty + zbase + zsB);
+            mbar_arrive(ze + zsA);
+            if (two) mbar_arrive(ze + zsB);
           }
-          ABX_WAIT(1, a_empty + asA, apA, 402);
-          if (two) ABX_WAIT(1, a_empty + asB, apB, 402);
+          ABX_WAIT(1, ae + asA, apA, 402);
+          if (two) ABX_WAIT(1, ae + asB, apB, 402);
           tc_fence_after();
           tmem_st16(lane_base + 16u * asA, vA);
           if (two) tmem_st16(lane_base + 16u * asB, vB);
           pendA = asA; pendB = asB;
         }
-        base0 += nr0; base1 += nr1; base2 += nr2;
       }
       hand_over();
     }
@@ -751,15 +734,15 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     __syncwarp();
     if (lane == 0) mbar_arrive(lsum_ready);
   } else {
-    // ---------------- attention over the value rows: thread = (row group rg: rows 10 rg .. 10 rg + 9, head h, dims 4 d4 ..) ----------------
+    // ---------------- attention over the value rows: thread = (head h, dims 4 d4 ..) x all 20 query rows ----------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsVal));
     const int t = threadIdx.x - kWarpVal * 32;
-    const bool worker = t < 2 * kH * (kVD / 4);
-    const int rg = worker ? t / (kH * (kVD / 4)) : 0, dg = worker ? t % (kH * (kVD / 4)) : 0;
+    const bool worker = t < kH * (kVD / 4);
+    const int dg = worker ? t : 0;
     const int h = dg / (kVD / 4), d4 = dg % (kVD / 4);
-    float2 acc[kHalfRows / 2][4];                    // [row pair][dim]: (row 2j, row 2j + 1)
+    float2 acc[kMaxRows / 2][4];                     // [row pair][dim]: (row 2j, row 2j + 1)
 #pragma unroll
-    for (int j = 0; j < kHalfRows / 2; ++j)
+    for (int j = 0; j < kMaxRows / 2; ++j)
 #pragma unroll
       for (int d = 0; d < 4; ++d) acc[j][d] = make_float2(0.f, 0.f);
 
@@ -768,8 +751,9 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       const int buf = c & 1, pb = c % kPD, nk = min(kChunk, N - c * kChunk);
       ABX_WAIT(0, kv_full + buf, (c >> 1) & 1, 701);
       ABX_WAIT(1, p_full + pb, (c / kPD) & 1, 702);
-      {
-        const float4* ap = reinterpret_cast<const float4*>(AL + ((size_t)pb * kH + h) * kPfRow + rg * 12);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {                  // rows 10 g .. 10 g + 9 live at [12 g, 12 g + 10) of a 24-float row
+        const float4* ap = reinterpret_cast<const float4*>(AL + ((size_t)pb * kH + h) * kPfRow + g * 12);
         const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
         const bool moved = (a0.x != 1.f) | (a0.y != 1.f) | (a0.z != 1.f) | (a0.w != 1.f) | (a1.x != 1.f) | (a1.y != 1.f) |
                            (a1.z != 1.f) | (a1.w != 1.f) | (a2.x != 1.f) | (a2.y != 1.f);
@@ -779,28 +763,31 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
 #pragma unroll
           for (int j = 0; j < 5; ++j)
 #pragma unroll
-            for (int d = 0; d < 4; ++d) { acc[j][d].x *= f[j].x; acc[j][d].y *= f[j].y; }
+            for (int d = 0; d < 4; ++d) { acc[5 * g + j][d].x *= f[j].x; acc[5 * g + j][d].y *= f[j].y; }
         }
       }
       const float* vbase = KVs + (size_t)buf * kChunk * kKVRow + kVOff + h * kVD + 4 * d4;
-      const float* pbase = PF + ((size_t)pb * kChunk * kH + h) * kPfRow + rg * 12;
+      const float* pbase = PF + ((size_t)pb * kChunk * kH + h) * kPfRow;
       auto one_key = [&](int kk) {
         const float4 v = *reinterpret_cast<const float4*>(vbase + kk * kKVRow);
-        const float4* pp = reinterpret_cast<const float4*>(pbase + kk * kH * kPfRow);
-        const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2];
-        const float2 pr[5] = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w), make_float2(p1.x, p1.y), make_float2(p1.z, p1.w),
-                              make_float2(p2.x, p2.y)};
         const float2 vx = make_float2(v.x, v.x), vy = make_float2(v.y, v.y), vz = make_float2(v.z, v.z), vw = make_float2(v.w, v.w);
+        const float4* pp = reinterpret_cast<const float4*>(pbase + kk * kH * kPfRow);
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          acc[j][0] = ffma2(pr[j], vx, acc[j][0]);
-          acc[j][1] = ffma2(pr[j], vy, acc[j][1]);
-          acc[j][2] = ffma2(pr[j], vz, acc[j][2]);
-          acc[j][3] = ffma2(pr[j], vw, acc[j][3]);
+        for (int g = 0; g < 2; ++g) {
+          const float4 p0 = pp[3 * g], p1 = pp[3 * g + 1], p2 = pp[3 * g + 2];
+          const float2 pr[5] = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w), make_float2(p1.x, p1.y), make_float2(p1.z, p1.w),
+                                make_float2(p2.x, p2.y)};
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            acc[5 * g + j][0] = ffma2(pr[j], vx, acc[5 * g + j][0]);
+            acc[5 * g + j][1] = ffma2(pr[j], vy, acc[5 * g + j][1]);
+            acc[5 * g + j][2] = ffma2(pr[j], vz, acc[5 * g + j][2]);
+            acc[5 * g + j][3] = ffma2(pr[j], vw, acc[5 * g + j][3]);
+          }
         }
       };
       if (nk == kChunk) {
-#pragma unroll
+#pragma unroll 2
         for (int kk = 0; kk < kChunk; ++kk) one_key(kk);
       } else {
         for (int kk = 0; kk < nk; ++kk) one_key(kk);
@@ -812,27 +799,31 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     if constexpr (kProf) { if (lane == 0) rp_.flush(prof, 5); }
     // ---- normalise, stage the 480 value outputs of every row, then write o_scalar / o_point / o_point_norm ----
     mbar_wait(lsum_ready, 0, 703);
-    asm volatile("bar.sync 1, 256;" ::: "memory");   // every value warp is done with the key/value buffers
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // every value warp is done with the key/value buffers
     float* OV = reinterpret_cast<float*>(sm + L.ov); // [R][480]
     if (worker) {
-      const float4* lp = reinterpret_cast<const float4*>(LINV + h * kPfRow + rg * 12);
-      const float4 i0v = lp[0], i1v = lp[1], i2v = lp[2];
-      const float inv[10] = {i0v.x, i0v.y, i0v.z, i0v.w, i1v.x, i1v.y, i1v.z, i1v.w, i2v.x, i2v.y};
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const int ra = rg * kHalfRows + 2 * j;
-        *reinterpret_cast<float4*>(OV + (size_t)ra * (kH * kVD) + h * kVD + 4 * d4) =
-            make_float4(acc[j][0].x * inv[2 * j], acc[j][1].x * inv[2 * j], acc[j][2].x * inv[2 * j], acc[j][3].x * inv[2 * j]);
-        *reinterpret_cast<float4*>(OV + (size_t)(ra + 1) * (kH * kVD) + h * kVD + 4 * d4) =
-            make_float4(acc[j][0].y * inv[2 * j + 1], acc[j][1].y * inv[2 * j + 1], acc[j][2].y * inv[2 * j + 1], acc[j][3].y * inv[2 * j + 1]);
+      for (int g = 0; g < 2; ++g) {
+        const float4* lp = reinterpret_cast<const float4*>(LINV + h * kPfRow + g * 12);
+        const float4 i0v = lp[0], i1v = lp[1], i2v = lp[2];
+        const float inv[10] = {i0v.x, i0v.y, i0v.z, i0v.w, i1v.x, i1v.y, i1v.z, i1v.w, i2v.x, i2v.y};
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int ra = g * kHalfRows + 2 * j;
+          const float2* a = acc[5 * g + j];
+          *reinterpret_cast<float4*>(OV + (size_t)ra * (kH * kVD) + h * kVD + 4 * d4) =
+              make_float4(a[0].x * inv[2 * j], a[1].x * inv[2 * j], a[2].x * inv[2 * j], a[3].x * inv[2 * j]);
+          *reinterpret_cast<float4*>(OV + (size_t)(ra + 1) * (kH * kVD) + h * kVD + 4 * d4) =
+              make_float4(a[0].y * inv[2 * j + 1], a[1].y * inv[2 * j + 1], a[2].y * inv[2 * j + 1], a[3].y * inv[2 * j + 1]);
+        }
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    for (int e = t; e < nvalid * kH * kSv; e += 256) {                                          // 'b i h c -> b i (h c)'  :115
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int e = t; e < nvalid * kH * kSv; e += kValThreads) {                                          // 'b i h c -> b i (h c)'  :115
       const int r = e / (kH * kSv), o = e % (kH * kSv);
       feats[((size_t)b * N + i0 + r) * kFeat + o] = OV[(size_t)r * (kH * kVD) + (o / kSv) * kVD + (o % kSv)];
     }
-    for (int e = t; e < nvalid * kH * kPv; e += 256) {
+    for (int e = t; e < nvalid * kH * kPv; e += kValThreads) {
       const int r = e / (kH * kPv), pi = e % (kH * kPv), hh = pi / kPv, p = pi % kPv;
       const size_t bn = (size_t)b * N + i0 + r;
       float Rm[9], tr[3], it[3], l[3];
@@ -986,7 +977,7 @@ int launch_ipa_fused(cudaStream_t s, int B, int N, const float* Qp, const float*
   while (zslots > 4 && smem_layout(N, zslots).total > 227 * 1024) --zslots;
   const Smem L = smem_layout(N, zslots);
   ABX_REQUIRE(L.total <= 227 * 1024, "ipa_fused: N=%d needs %u bytes of shared memory", N, L.total);
-  ABX_REQUIRE(zslots / 2 >= (R + 1) / 2, "ipa_fused: N=%d leaves %d z slots, too few for %d-row tiles", N, zslots, R);
+  ABX_REQUIRE(zslots / kCols >= (R + kCols - 1) / kCols, "ipa_fused: N=%d leaves %d z slots, too few for %d-row tiles", N, zslots, R);
   unsigned long long* prof = nullptr;
   if (g_prof_on) ABX_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&prof), g_ipa_prof));
   auto* kernel = g_prof_on ? ipa_fused_kernel<true> : ipa_fused_kernel<false>;

@@ -50,15 +50,7 @@ def main():
     cfg = bench.model_config()
     fd = FullDiffuser(cfg['diffuser'])
     model = load_seeded_(ScoreNetwork(cfg['model'], fd), 0).to(dev).eval()
-    torch.manual_seed(a.seed)
     raw = synthetic_complex(n_antigen=a.n_antigen, seed=0, batch_size=1)
-    batch0 = F_.FeatureBuilder(bench.feature_config(cfg, dev, fd)).build({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in raw.items()})
-    N = batch0['seq'].shape[1]
-    grid = np.linspace(1.0 / a.num_t, 1.0, a.num_t)[::-1]
-    dt = torch.tensor(1.0 / a.num_t)
-    ones = torch.ones(1, device=dev)
-    diffuse_mask = (1 - batch0['fixed_mask']) * batch0['atom14_gt_exists'][..., 0]
-
     # ---------------- reference arm: the reference's own ScoreNetwork / get_prev / FullDiffuser on the GPU ----------------
     from oracle import ref_harness, ref_runner
     assert ref_runner.available(), 'oracle/_ref is missing (python oracle/build_ref.py in the build container)'
@@ -67,9 +59,37 @@ def main():
     from abx.model.abx import ScoreNetwork as RefNet, get_prev as ref_get_prev
     from diffuser.full_diffuser import FullDiffuser as RefDiffuser
     import inference as ref_inf
-    rcfg, _ = ref_harness.load_config(cache_dir=os.path.join(ref_runner.REF, 'igso3_cache') + os.sep)
+    rcfg, _raw = ref_harness.load_config(cache_dir=os.path.join(ref_runner.REF, 'igso3_cache') + os.sep)
     rfd = RefDiffuser.get(rcfg.diffuser)
     rmodel = load_seeded_(RefNet(rcfg.model, rfd), 0).to(dev).eval()
+    # the start state (features + t = 1 prior draw) comes from the REFERENCE's FeatureBuilder (it also carries the keys only the
+    # reference's unused heads read, e.g. pseudo_beta); both arms start from clones of it
+    from abx.model.features import FeatureBuilder as RefFeatureBuilder
+    with open(os.path.join(ref_runner.REF, 'config', 'config_data_feature.json')) as f:
+        rfeats = json.load(f)
+    for name, args in rfeats:
+        if 'device' in args:
+            args['device'] = 'cpu'
+        if 'diffuse' in name:
+            args['diff_conf'] = _raw['diffuser']
+            args.pop('optimize_steps', None)
+            args['generate_area'] = 'H3'
+    torch.manual_seed(a.seed)
+    cpu_batch = RefFeatureBuilder(rfeats, is_training=False).build(raw)
+
+    def to_dev(v):
+        if torch.is_tensor(v):
+            return v.to(dev)
+        if isinstance(v, tuple) and v and torch.is_tensor(v[0]):
+            return tuple(x.to(dev) for x in v)
+        return v
+    batch0 = {k: to_dev(v) for k, v in cpu_batch.items()}
+
+    N = batch0['seq'].shape[1]
+    grid = np.linspace(1.0 / a.num_t, 1.0, a.num_t)[::-1]
+    dt = torch.tensor(1.0 / a.num_t)
+    ones = torch.ones(1, device=dev)
+    diffuse_mask = (1 - batch0['fixed_mask']) * batch0['atom14_gt_exists'][..., 0]
 
     def run(arm):
         b = clone(batch0)
