@@ -112,7 +112,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // a readable record, abx_ipa_watchdog_read) instead of hanging the device.
 __device__ unsigned long long g_ipa_watchdog[8];
 __device__ unsigned long long g_ipa_prof[64];
-template <bool kSleep = false, bool kTime = false>
+template <bool kSleep = false, bool kTime = false, bool kSpin = false>
 __device__ __forceinline__ unsigned mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {   // kTime: returns the cycles spent waiting
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
@@ -128,11 +128,19 @@ __device__ __forceinline__ unsigned mbar_wait(uint64_t* bar, uint32_t parity, in
   // working warps of the same scheduler need; the watchdog is only consulted when a suspension timed out.
   const uint32_t hint_ns = kSleep ? 200000u : 20000u;
   do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(addr), "r"(parity), "r"(hint_ns) : "memory");
+    if constexpr (kSpin) {                           // latency-critical warps (producers, issuers, converters): plain polling
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(addr), "r"(parity), "r"(hint_ns) : "memory");
+    }
     if (!ok) {
       if (*reinterpret_cast<volatile unsigned long long*>(&g_ipa_watchdog[0]) != 0ull) break;
       if (clock64() - t1 > 500000000ll) {
@@ -310,6 +318,11 @@ __global__ void __launch_bounds__(256) ipa_pack_nodes_kernel(int B, int N, const
     if constexpr (kProf) rp_.w[i] += mbar_wait<false, true>(__VA_ARGS__);  \
     else mbar_wait<false, false>(__VA_ARGS__);                             \
   } while (0)
+#define ABX_WAIT_SPIN(i, ...)                                                    \
+  do {                                                                           \
+    if constexpr (kProf) rp_.w[i] += mbar_wait<false, true, true>(__VA_ARGS__);  \
+    else mbar_wait<false, false, true>(__VA_ARGS__);                             \
+  } while (0)
 
 template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -396,39 +409,63 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
   const int wg = warp >> 2;
   if (wg == kWgCtl) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
-    if (warp == kWarpZ && lane < nvalid) {
-      // ---------------- z producer: lane r streams query row r (z is an input of the whole layer: no wait for the
-      // preceding kernels).  One lane alone cannot issue 20 bulk copies per chunk fast enough; 20 lanes issue side by side.
-      const uint8_t* zb = reinterpret_cast<const uint8_t*>(z + ((size_t)b * N + i0 + lane) * (size_t)N * kCz);
+    if (warp == kWarpZ) {
+      // ---------------- producers: lane r streams query row r of z (z is an input of the whole layer: no wait for the
+      // preceding kernels), lane 31 the key/value + pair-bias chunks.  The warp stays converged: every lane polls its own slot
+      // without blocking, the lanes whose slot is free issue their copy in the same pass, the others retry.  (Independent
+      // per-lane loops would be executed one lane after the other: 20 lanes x ~50 instructions per chunk is the kernel's pace.)
+      const bool zlane = lane < nvalid, kvlane = lane == 31;
+      const uint8_t* zb = reinterpret_cast<const uint8_t*>(z + ((size_t)b * N + i0 + (zlane ? lane : 0)) * (size_t)N * kCz);
       const int col = lane % kCols, zbase = zring_base(zslots, col), zn = zring_size(zslots, col);   // this row's ring
       const int nw = col_rows(nvalid, col);          // rows of the tile in that ring = ring positions per chunk (<= zn)
-      int pos = lane / kCols;                        // ring position of (chunk c, this row), modulo zn
-      uint32_t ph = 1u;                              // parity of the "empty" phase that precedes the slot's next use
-      RoleProf rp_; if constexpr (kProf) rp_.start();
-      for (int c = 0; c < nchunks; ++c) {
-        if (c > 0) {                                 // chunk 0 was issued before the grid-dependency wait
-          const uint32_t bytes = (uint32_t)min(kChunk, N - c * kChunk) * kCz * 4;
-          const int slot = zbase + pos;
-          ABX_WAIT(0, z_empty + slot, ph, 101);
-          mbar_expect_tx(z_full + slot, bytes);
-          bulk_g2s(ZR + (size_t)slot * kZSlotBytes, zb + (size_t)c * kZSlotBytes, bytes, z_full + slot);
+      int pos = lane / kCols + nw;                   // ring position of (chunk c, this row), modulo zn; chunk 0 went out before
+      uint32_t ph = 1u;                              // the grid-dependency wait; parity of the "empty" phase before the slot's use
+      if (pos >= zn) { pos -= zn; ph ^= 1u; }
+      int c = zlane ? 1 : 0;                         // next chunk this lane issues
+      const bool has_work = zlane || kvlane;
+      const long long t_start = clock64();
+      for (;;) {
+        const bool work = has_work && c < nchunks;
+        if (!__any_sync(0xffffffffu, work)) break;
+        bool ready = false;
+        if (work) {
+          uint64_t* bar = zlane ? (z_empty + zbase + pos) : (kv_empty + (c & 1));
+          const uint32_t par = zlane ? ph : (uint32_t)(((c >> 1) & 1) ^ 1);
+          uint32_t ok;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}"
+              : "=r"(ok) : "r"(smem_u32(bar)), "r"(par) : "memory");
+          ready = ok != 0u;
         }
-        pos += nw;
-        if (pos >= zn) { pos -= zn; ph ^= 1u; }
+        if (ready) {
+          const int nk = min(kChunk, N - c * kChunk);
+          if (zlane) {
+            const int slot = zbase + pos;
+            const uint32_t bytes = (uint32_t)nk * kCz * 4;
+            mbar_expect_tx(z_full + slot, bytes);
+            bulk_g2s(ZR + (size_t)slot * kZSlotBytes, zb + (size_t)c * kZSlotBytes, bytes, z_full + slot);
+            pos += nw;
+            if (pos >= zn) { pos -= zn; ph ^= 1u; }
+          } else {
+            const int buf = c & 1;
+            const uint32_t kvb = (uint32_t)nk * kKVRow * 4, bb = (uint32_t)nvalid * kBiasRow * 4;
+            mbar_expect_tx(kv_full + buf, kvb + bb);
+            bulk_g2s(KVs + (size_t)buf * kChunk * kKVRow, KVp + ((size_t)b * N + c * kChunk) * kKVRow, kvb, kv_full + buf);
+            bulk_g2s(BSs + (size_t)buf * kMaxRows * kBiasRow, bias + (((size_t)b * nchunks + c) * N + i0) * kBiasRow, bb, kv_full + buf);
+          }
+          ++c;
+        } else if (work && clock64() - t_start > 1000000000ll) {   // watchdog (same record as mbar_wait's)
+          if (atomicCAS(&g_ipa_watchdog[0], 0ull, 1ull) == 0ull) {
+            g_ipa_watchdog[1] = zlane ? 101ull : 201ull; g_ipa_watchdog[2] = blockIdx.x; g_ipa_watchdog[3] = threadIdx.x;
+            __threadfence();
+          }
+          c = nchunks;
+        } else if (*reinterpret_cast<volatile unsigned long long*>(&g_ipa_watchdog[0]) != 0ull) {
+          c = nchunks;
+        }
       }
-      if constexpr (kProf) { if (lane == 0) rp_.flush(prof, 0); }
-    } else if (warp == kWarpZ && lane == 31) {
-      // ---------------- key/value + pair-bias producer (an independently scheduled lane of the same warp) ----------------
-      RoleProf rp_; if constexpr (kProf) rp_.start();
-      for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1, nk = min(kChunk, N - c * kChunk);
-        ABX_WAIT(0, kv_empty + buf, ((c >> 1) & 1) ^ 1, 201);
-        const uint32_t kvb = (uint32_t)nk * kKVRow * 4, bb = (uint32_t)nvalid * kBiasRow * 4;
-        mbar_expect_tx(kv_full + buf, kvb + bb);
-        bulk_g2s(KVs + (size_t)buf * kChunk * kKVRow, KVp + ((size_t)b * N + c * kChunk) * kKVRow, kvb, kv_full + buf);
-        bulk_g2s(BSs + (size_t)buf * kMaxRows * kBiasRow, bias + (((size_t)b * nchunks + c) * N + i0) * kBiasRow, bb, kv_full + buf);
-      }
-      if constexpr (kProf) { rp_.flush(prof, 1); }
     } else if (warp >= kWarpMma && warp < kWarpMma + kIssuers) {
       // ---------------- MMA issuers: warps 1, 2, 3 take the query rows r = 0, 1, 2 (mod 3) ----------------
       // The whole warp walks the loop (uniform control flow keeps the operand addresses in uniform registers); one elected
@@ -442,7 +479,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
       int seq = 0;                                   // items issued so far = position in A ring mi
       for (int c = 0; c < nchunks; ++c) {
         const int pb = c % kPD;
-        ABX_WAIT(0, p_full + pb, (c / kPD) & 1, 301);
+        ABX_WAIT_SPIN(0, p_full + pb, (c / kPD) & 1, 301);
         tc_fence_after();
         const unsigned rm = *reinterpret_cast<volatile unsigned*>(resc + (c & 3)) & my_rows;
         const uint32_t acc = c > 0 ? 1u : 0u;
@@ -471,7 +508,7 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
         const uint32_t pt = ptile0 + (uint32_t)(pb * kMaxRows) * kPTileBytes;
         for (int r = mi; r < nvalid; r += kIssuers, ++seq) {
           const int aslot = 4 * mi + (seq & 3);
-          ABX_WAIT(1, a_full + aslot, (uint32_t)(seq >> 2) & 1u, 302);
+          ABX_WAIT_SPIN(1, a_full + aslot, (uint32_t)(seq >> 2) & 1u, 302);
           tc_fence_after();
           const uint32_t d = tmem_base + 16u * r;
           const uint32_t a_hi = tmem_base + kACol0 + 16u * aslot, a_lo = a_hi + 8u;
@@ -556,10 +593,10 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
           const uint32_t zpB = zph;
           if (two) { if (++zpos == zn) { zpos = 0; zph ^= 1u; } }
           uint32_t vA[16], vB[16];                  // [0, 8): hi = the raw words, [8, 16): lo — one 16-column tcgen05.st per item
-          ABX_WAIT(0, zf + zsA, zpA, 401);
+          ABX_WAIT_SPIN(0, zf + zsA, zpA, 401);
           load_item(zsA, nk, vA);
           if (two) {
-            ABX_WAIT(0, zf + zsB, zpB, 401);
+            ABX_WAIT_SPIN(0, zf + zsB, zpB, 401);
             load_item(zsB, nk, vB);
           }
           hand_over();                               // overlaps the shared-memory round trip of this round's loads
@@ -570,8 +607,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
             mbar_arrive(ze + zsA);
             if (two) mbar_arrive(ze + zsB);
           }
-          ABX_WAIT(1, ae + asA, apA, 402);
-          if (two) ABX_WAIT(1, ae + asB, apB, 402);
+          ABX_WAIT_SPIN(1, ae + asA, apA, 402);
+          if (two) ABX_WAIT_SPIN(1, ae + asB, apB, 402);
           tc_fence_after();
           tmem_st16(lane_base + 16u * asA, vA);
           if (two) tmem_st16(lane_base + 16u * asB, vB);
