@@ -257,56 +257,60 @@ __device__ __forceinline__ int pf_row(int r) { return r + 2 * (r / kHalfRows); }
 // pack: row of the fused node projection [q_scalar 192 | kv_scalar 384 | q_point_local 144 | kv_point_local 432]
 // (folding.py:69-86) -> packed queries Qp [B,N,12,28] = (q_s * sqrt(1/48), 4 query points in the global frame) and
 // packed keys / values KVp [B,N,816] = 12 x (k_s 16, 4 key points) then 12 x (v_s 16, 8 value points), points
-// moved to the global frame (r3.rigids_apply, r3.py:9-16).  One thread per (b, n, h, item): items 0-3 / 4-7 / 8-11 =
-// float4 groups of the q / k / v scalars, 12-15 / 16-19 / 20-27 = q / k / v points.
+// moved to the global frame (r3.rigids_apply, r3.py:9-16).  64 threads per residue: the projection row is staged in shared
+// memory with coalesced reads, every thread then writes consecutive output floats.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kProj = 1152, kOffKV = kH * kSqk, kOffQP = kOffKV + kH * (kSqk + kSv), kOffKVP = kOffQP + 3 * kH * kPqk;
-constexpr int kPackItems = 3 * (kSqk / 4) + 2 * kPqk + kPv;   // 28
+constexpr int kPackRes = 4, kPackThreads = 64 * kPackRes;   // residues per CTA, 64 threads each
 
-__global__ void __launch_bounds__(256) ipa_pack_nodes_kernel(int B, int N, const float* __restrict__ proj,
-                                                             const float* __restrict__ rots, const float* __restrict__ trans,
-                                                             float* __restrict__ Qp, float* __restrict__ KVp) {
+__global__ void __launch_bounds__(kPackThreads) ipa_pack_nodes_kernel(int BN, const float* __restrict__ proj,
+                                                                      const float* __restrict__ rots, const float* __restrict__ trans,
+                                                                      float* __restrict__ Qp, float* __restrict__ KVp) {
+  __shared__ __align__(16) float row_s[kPackRes][kProj];
+  __shared__ float rt_s[kPackRes][12];
   griddep_wait();                                    // proj comes from the node GEMM launched just before
   griddep_launch_dependents();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * N * kH * kPackItems) return;
-  const int item = idx % kPackItems, rest = idx / kPackItems;
-  const int h = rest % kH, bn = rest / kH;
-  const float* row = proj + (size_t)bn * kProj;
-  float* q = Qp + (size_t)bn * kQRow + h * kQK;
-  float* k = KVp + (size_t)bn * kKVRow + h * kQK;
-  float* v = KVp + (size_t)bn * kKVRow + kVOff + h * kVD;
-  if (item < 12) {                                   // scalar channels, 4 at a time
-    const int grp = item >> 2, c = 4 * (item & 3);
-    if (grp == 0) {
-      const float w_scalar = sqrtf(1.0f / (3.0f * kSqk));                       // folding.py:59,79
-      const float4 s = *reinterpret_cast<const float4*>(row + h * kSqk + c);
-      *reinterpret_cast<float4*>(q + c) = make_float4(s.x * w_scalar, s.y * w_scalar, s.z * w_scalar, s.w * w_scalar);
-    } else if (grp == 1) {
-      *reinterpret_cast<float4*>(k + c) = *reinterpret_cast<const float4*>(row + kOffKV + h * (kSqk + kSv) + c);
+  const int sub = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int bn = blockIdx.x * kPackRes + sub;
+  const bool live = bn < BN;
+  if (live) {                                        // coalesced 16-byte reads of the projection row; frame of the residue
+    const float4* src = reinterpret_cast<const float4*>(proj + (size_t)bn * kProj);
+    for (int k = t; k < kProj / 4; k += 64) reinterpret_cast<float4*>(row_s[sub])[k] = src[k];
+    if (t < 9) rt_s[sub][t] = __ldg(rots + (size_t)bn * 9 + t);
+    else if (t < 12) rt_s[sub][t] = __ldg(trans + (size_t)bn * 3 + (t - 9));
+  }
+  __syncthreads();
+  if (!live) return;
+  const float* row = row_s[sub];
+  const float* Rm = rt_s[sub];
+  const float* tr = rt_s[sub] + 9;
+  // one global point coordinate: component k of R l + t, l = the point's three local coordinates ('(r n)' layout, stride)
+  auto point = [&](const float* l, int stride, int k) {
+    return tr[k] + (Rm[3 * k] * l[0] + Rm[3 * k + 1] * l[stride] + Rm[3 * k + 2] * l[2 * stride]);
+  };
+  const float w_scalar = sqrtf(1.0f / (3.0f * kSqk));                           // folding.py:59,79
+  float* q = Qp + (size_t)bn * kQRow;
+  for (int e = t; e < kQRow; e += 64) {              // packed queries: per head 16 scalars * w_scalar, 4 global points
+    const int h = e / kQK, o = e % kQK;
+    float v;
+    if (o < kSqk) v = row[h * kSqk + o] * w_scalar;
+    else { const int p = (o - kSqk) / 3, k = (o - kSqk) % 3; v = point(row + kOffQP + h * kPqk + p, kH * kPqk, k); }
+    q[e] = v;
+  }
+  float* kv = KVp + (size_t)bn * kKVRow;
+  for (int e = t; e < kKVRow; e += 64) {             // packed keys (12 x 28) then values (12 x 40)
+    float v;
+    if (e < kVOff) {
+      const int h = e / kQK, o = e % kQK;
+      if (o < kSqk) v = row[kOffKV + h * (kSqk + kSv) + o];
+      else { const int p = (o - kSqk) / 3, k = (o - kSqk) % 3; v = point(row + kOffKVP + h * (kPqk + kPv) + p, kH * (kPqk + kPv), k); }
     } else {
-      *reinterpret_cast<float4*>(v + c) = *reinterpret_cast<const float4*>(row + kOffKV + h * (kSqk + kSv) + kSqk + c);
+      const int h = (e - kVOff) / kVD, o = (e - kVOff) % kVD;
+      if (o < kSv) v = row[kOffKV + h * (kSqk + kSv) + kSqk + o];
+      else { const int p = (o - kSv) / 3, k = (o - kSv) % 3; v = point(row + kOffKVP + h * (kPqk + kPv) + kPqk + p, kH * (kPqk + kPv), k); }
     }
-    return;
+    kv[e] = v;
   }
-  // one point: local coordinates are channel-major '(r n)', n = (h p)   folding.py:82,91,93
-  const float* l;
-  int stride;
-  float* dst;
-  if (item < 16) {
-    const int p = item - 12;
-    l = row + kOffQP + h * kPqk + p; stride = kH * kPqk; dst = q + kSqk + 3 * p;
-  } else {
-    const int p = item - 16;                         // per head: 4 key points then 8 value points
-    l = row + kOffKVP + h * (kPqk + kPv) + p; stride = kH * (kPqk + kPv);
-    dst = (p < kPqk) ? (k + kSqk + 3 * p) : (v + kSv + 3 * (p - kPqk));
-  }
-  const float lx = l[0], ly = l[stride], lz = l[2 * stride];
-  const float* Rm = rots + (size_t)bn * 9;
-  const float* t = trans + (size_t)bn * 3;
-  dst[0] = __ldg(t + 0) + (__ldg(Rm + 0) * lx + __ldg(Rm + 1) * ly + __ldg(Rm + 2) * lz);
-  dst[1] = __ldg(t + 1) + (__ldg(Rm + 3) * lx + __ldg(Rm + 4) * ly + __ldg(Rm + 5) * lz);
-  dst[2] = __ldg(t + 2) + (__ldg(Rm + 6) * lx + __ldg(Rm + 7) * ly + __ldg(Rm + 8) * lz);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -893,47 +897,55 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
 // ---------------------------------------------------------------------------------------------------
 // chunked key-major pair bias: out[b][c][i][12 k + h] = sqrt(1/3) (z[b,i,8c+k,:] . w[h,:] + b[h])   folding.py:101-104
 // One CTA per (b, i, 64-key tile): the z tile is staged in shared memory (row stride 132 floats: conflict-free
-// float4 reads with lanes on consecutive keys), thread = (key, group of 3 heads).
+// float4 reads with lanes on consecutive keys), thread = (key, group of 6 heads).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kBiasJ = 64, kZld = kCz + 4;
+constexpr int kBiasJ = 64, kZld = kCz + 4, kBiasThreads = 128;
 
-__global__ void __launch_bounds__(256) ipa_pair_bias_chunked_kernel(int N, const float* __restrict__ z,
-                                                                    const float* __restrict__ w_pair,
-                                                                    const float* __restrict__ b_pair, float* __restrict__ bias) {
+__global__ void __launch_bounds__(kBiasThreads) ipa_pair_bias_chunked_kernel(int N, const float* __restrict__ z,
+                                                                             const float* __restrict__ w_pair,
+                                                                             const float* __restrict__ b_pair,
+                                                                             float* __restrict__ bias) {
   __shared__ __align__(16) float zs[kBiasJ * kZld];
   __shared__ __align__(16) float ws[kH * kCz];
   const int j0 = blockIdx.x * kBiasJ, i = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x;
   const int nchunks = (N + kChunk - 1) / kChunk;
-  for (int k = tid; k < kH * kCz / 4; k += 256)
+  for (int k = tid; k < kH * kCz / 4; k += kBiasThreads)
     reinterpret_cast<float4*>(ws)[k] = __ldg(reinterpret_cast<const float4*>(w_pair) + k);
   const float4* zrow = reinterpret_cast<const float4*>(z + (((size_t)b * N + i) * N + j0) * kCz);
   const int nj = min(kBiasJ, N - j0);
-  for (int k = tid; k < nj * (kCz / 4); k += 256) {
+#pragma unroll 4
+  for (int k = tid; k < nj * (kCz / 4); k += kBiasThreads) {
     const int jj = k / (kCz / 4), c4 = k % (kCz / 4);
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(zrow + k));
     *reinterpret_cast<float4*>(&zs[jj * kZld + 4 * c4]) = v;
   }
   __syncthreads();
-  const int jj = tid % kBiasJ, hg = tid / kBiasJ;     // heads 3*hg .. 3*hg+2
+  // thread = (key, 6 heads): one 16-byte z read feeds 24 multiply-adds (12 FFMA2); the weight reads are warp-wide broadcasts
+  const int jj = tid % kBiasJ, hg = tid / kBiasJ;     // heads 6 hg .. 6 hg + 5
   if (jj >= nj) return;
-  float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll 8
+  float2 acc[6];
+#pragma unroll
+  for (int u = 0; u < 6; ++u) acc[u] = make_float2(0.f, 0.f);
+#pragma unroll 4
   for (int c = 0; c < kCz; c += 4) {
     const float4 zv = *reinterpret_cast<const float4*>(&zs[jj * kZld + c]);
+    const float2 za = make_float2(zv.x, zv.y), zb = make_float2(zv.z, zv.w);
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const float4 wv = *reinterpret_cast<const float4*>(&ws[(3 * hg + u) * kCz + c]);
-      acc[u] = fmaf(zv.x, wv.x, acc[u]); acc[u] = fmaf(zv.y, wv.y, acc[u]);
-      acc[u] = fmaf(zv.z, wv.z, acc[u]); acc[u] = fmaf(zv.w, wv.w, acc[u]);
+    for (int u = 0; u < 6; ++u) {
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[(6 * hg + u) * kCz + c]);
+      acc[u] = ffma2(za, make_float2(wv.x, wv.y), acc[u]);
+      acc[u] = ffma2(zb, make_float2(wv.z, wv.w), acc[u]);
     }
   }
   const float w_pair_scale = sqrtf(1.0f / 3.0f);
   const int j = j0 + jj;
-  float* dst = bias + (((size_t)b * nchunks + j / kChunk) * N + i) * kBiasRow + (j % kChunk) * kH + 3 * hg;
+  float* dst = bias + (((size_t)b * nchunks + j / kChunk) * N + i) * kBiasRow + (j % kChunk) * kH + 6 * hg;
 #pragma unroll
-  for (int u = 0; u < 3; ++u) dst[u] = w_pair_scale * (acc[u] + __ldg(b_pair + 3 * hg + u));
+  for (int u = 0; u < 6; u += 2)
+    *reinterpret_cast<float2*>(dst + u) = make_float2(w_pair_scale * ((acc[u].x + acc[u].y) + __ldg(b_pair + 6 * hg + u)),
+                                                      w_pair_scale * ((acc[u + 1].x + acc[u + 1].y) + __ldg(b_pair + 6 * hg + u + 1)));
 }
 
 // Tile height: time ~ rounds * (R + 6.4) — R rows of z per tile plus the tile's key / value chunks (3264 B per key
@@ -991,14 +1003,14 @@ size_t ipa_fused_kvp_floats(int B, int N) { return (size_t)B * N * kKVRow; }
 size_t ipa_pair_bias_floats(int B, int N) { return (size_t)B * ceil_div(N, kChunk) * N * kBiasRow; }
 
 int launch_ipa_pair_bias(cudaStream_t s, int B, int N, const float* z, const float* w_pair, const float* b_pair, float* bias) {
-  ipa_pair_bias_chunked_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), 256, 0, s>>>(N, z, w_pair, b_pair, bias);
+  ipa_pair_bias_chunked_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), kBiasThreads, 0, s>>>(N, z, w_pair, b_pair, bias);
   count_launch();
   return check_launch("ipa_pair_bias_chunked_kernel");
 }
 
 int launch_ipa_pack_nodes(cudaStream_t s, int B, int N, const float* proj, const float* rots, const float* trans,
                           float* Qp, float* KVp) {
-  const cudaError_t le = launch_kernel(ipa_pack_nodes_kernel, dim3(ceil_div(B * N * kH * kPackItems, 256)), dim3(256), 0, s, B, N,
+  const cudaError_t le = launch_kernel(ipa_pack_nodes_kernel, dim3(ceil_div(B * N, kPackRes)), dim3(kPackThreads), 0, s, B * N,
                                        proj, rots, trans, Qp, KVp);
   count_launch();
   if (le != cudaSuccess) { set_error("launch of ipa_pack_nodes_kernel failed: %s", cudaGetErrorString(le)); return ABX_ERR_CUDA; }
