@@ -41,17 +41,27 @@ def parse():
     ap.add_argument('--samples-per-step', type=int, default=8, help='independent samples batched per GPU per step')
     ap.add_argument('--n-antigen', type=int, default=120, help='antigen residues (N = 230 + this)')
     ap.add_argument('--num-t', type=int, default=NUM_T)
+    ap.add_argument('--mode', default='design', choices=['design', 'optimize'],
+                    help="optimize = BASELINE config 4: start from forward_marginal(t = optimize_steps / T), run the remaining grid")
+    ap.add_argument('--generate-area', default='H3', help='H3 (design configs) or cdrs (all six CDRs, optimize config)')
+    ap.add_argument('--optimize-steps', type=int, default=20)
     ap.add_argument('--cpu-steps', type=int, default=1, help='reverse iterations timed for the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cuda-graph', type=int, default=1, help='replay the reverse iteration as a CUDA graph')
     return ap.parse_args()
 
 
+def n_forwards(a):
+    """ScoreNetwork forwards per sample: self-conditioning call + one per grid point (design: T; optimize: the points <= t0)."""
+    return (a.num_t if a.mode == 'design' else a.optimize_steps) + 1
+
+
 def workload_config(a, n_res):
-    return {'workload': f'synthetic H120+L110+A{a.n_antigen} complex (N={n_res}), generate_area=H3, T={a.num_t}, '
+    mode = '' if a.mode == 'design' else f', mode=optimize from t={a.optimize_steps}/{a.num_t} ({a.optimize_steps - 1} reverse steps + x0 call)'
+    return {'workload': f'synthetic H120+L110+A{a.n_antigen} complex (N={n_res}), generate_area={a.generate_area}, T={a.num_t}{mode}, '
                         f'num_recycle=2, ESM disabled, seeded random weights',
             'n_res': n_res, 'num_t': a.num_t, 'samples_per_gpu_per_step': a.samples_per_step,
-            'model_forwards_per_sample': a.num_t + 1, 'cuda_graph': bool(a.cuda_graph), 'ipa_layer_calls_per_sample': 24 * (a.num_t + 1),
+            'model_forwards_per_sample': n_forwards(a), 'cuda_graph': bool(a.cuda_graph), 'ipa_layer_calls_per_sample': 24 * n_forwards(a),
             'parallelism': f'dp{a.gpus} (independent samples per rank, no data-path collective)',
             'l2': 'pair activations of one batched IPA call (samples_per_step x 62.7 MB) exceed the 126 MB L2'}
 
@@ -64,15 +74,20 @@ def model_config():
     return cfg
 
 
-def feature_config(cfg, device, diffuser=None):
+def feature_config(cfg, device, diffuser=None, args=None):
     feats = json.load(open(os.path.join(ROOT, 'abx_b200', 'config', 'config_data_feature.json')))
     for name, kw in feats:
         if 'device' in kw:
             kw['device'] = device
         if name == 'make_diffuser_features':
-            kw['diff_conf'] = cfg['diffuser']
+            kw['diff_conf'] = dict(cfg['diffuser'])
             kw.pop('optimize_steps', None)
             kw['diffuser'] = diffuser
+            if args is not None:
+                kw['generate_area'] = args.generate_area
+                kw['diff_conf']['inference_step'] = args.num_t
+                if args.mode == 'optimize':             # features.py:194-203: noised start at t = opt_step / inference_step
+                    kw['diff_conf']['opt_step'] = args.optimize_steps
     return feats
 
 
@@ -279,7 +294,7 @@ def run_b200(a):
             t = host[k].to(dev)
             dist.broadcast(t, 0)
             host[k].copy_(t.cpu())
-    feat_cfg = feature_config(cfg, dev, fd)
+    feat_cfg = feature_config(cfg, dev, fd, a)
     static_cfg, diff_cfg = feat_cfg[:-1], feat_cfg[-1:]
 
     def features_from_host():
@@ -320,7 +335,7 @@ def run_b200(a):
         torch.manual_seed(1000 + step * world + rank)
         base = features_from_host() if e2e else {k: v for k, v in resident.items()}
         batch = F_.FeatureBuilder(diff_cfg).build(dict(base))                          # t = 1 prior draw
-        traj, _ = sampler.sample_loop(batch, cfg, fd, model, mode='design', num_t=a.num_t, generator=gen,
+        traj, _ = sampler.sample_loop(batch, cfg, fd, model, mode=a.mode, num_t=a.num_t, generator=gen,
                                       cuda_graph=use_graph[0])
         atom14 = traj[-1]['atom14_results'].contiguous()
         if world > 1:
@@ -360,7 +375,7 @@ def run_b200(a):
     instrument(False)
     launches = torch.tensor([lib.launch_count()], device=dev, dtype=torch.int64)
     if use_graph[0]:        # launches recorded while capturing replay once per reverse iteration
-        launches = launches + (a.num_t - 2) * getattr(sampler.GraphedReverseStep, 'last_captured_launches', 0) * a.steps
+        launches = launches + (n_forwards(a) - 3) * getattr(sampler.GraphedReverseStep, 'last_captured_launches', 0) * a.steps
     if world > 1:
         dist.all_reduce(launches)
     clock_info = clocks.stop() if rank == 0 else None
