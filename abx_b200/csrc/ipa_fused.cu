@@ -598,11 +598,9 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
           if (two) { if (++zpos == zn) { zpos = 0; zph ^= 1u; } }
           uint32_t vA[16], vB[16];                  // [0, 8): hi = the raw words, [8, 16): lo — one 16-column tcgen05.st per item
           ABX_WAIT_SPIN(0, zf + zsA, zpA, 401);
-          load_item(zsA, nk, vA);
-          if (two) {
-            ABX_WAIT_SPIN(0, zf + zsB, zpB, 401);
-            load_item(zsB, nk, vB);
-          }
+          if (two) ABX_WAIT_SPIN(0, zf + zsB, zpB, 401);
+          load_item(zsA, nk, vA);                    // 16 independent loads in flight
+          if (two) load_item(zsB, nk, vB);
           hand_over();                               // overlaps the shared-memory round trip of this round's loads
           low_part(vA);
           if (two) low_part(vB);

@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 COLS = [('time us', 'gpu__time_duration.sum', 1.0), ('DRAM read MB', 'dram__bytes_read.sum', 1.0), ('DRAM write MB', 'dram__bytes_write.sum', 1.0),
-        ('DRAM %', 'dram__throughput.avg.pct_of_peak_sustained_elapsed', 1.0), ('SM %', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 1.0),
+        ('DRAM active %', 'dram__cycles_active.avg.pct_of_peak_sustained_elapsed', 1.0), ('SM %', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 1.0),
         ('issue active %', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 1.0),
         ('warps active %', 'sm__warps_active.avg.pct_of_peak_sustained_active', 1.0), ('regs', 'launch__registers_per_thread', 1.0),
         ('tensor pipe %', 'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 1.0),
