@@ -355,7 +355,19 @@ static int launch_attention_mma(cudaStream_t st, int B, int S, int L, int H, con
 
 }  // namespace abx
 
-// impl: 0 = tensor-core kernel (default for D % 8 == 0), 1 = SIMT kernel
+namespace abx {
+template <int D>
+int launch_attention_tc5(cudaStream_t st, int B, int S, int L, int H, const float* q, const float* k, const float* v, int ld,
+                         const float* bias, const float* key_mask, const float* gate, float* out);
+// shared memory of the tcgen05 kernel (attention_tc5.cu): Q, K tile and V^T tile as hi / lo operand tiles + the key mask
+static size_t tc5_smem_bytes(int L, int D) {
+  const size_t q = (size_t)(D / 4) * (128 * 16 + 16), k = (size_t)(D / 4) * (64 * 16 + 16), v = (size_t)16 * (D * 16 + 16);
+  return 2 * (q + k + v) + (size_t)((L + 63) / 64) * 64 * 4 + 64;
+}
+}  // namespace abx
+
+// impl: 0 = tcgen05 kernel (attention_tc5.cu; falls back to 2 when its operand tiles do not fit 113 KB, i.e. D = 64),
+//       1 = SIMT kernel, 2 = mma.sync kernel
 extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, int D, const float* q, const float* k,
                                        const float* v, int ld, const float* bias, const float* key_mask, const float* gate,
                                        float* out) {
@@ -371,6 +383,13 @@ extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int
               "abx_pair_attention: q, k, v, out must be 16-byte aligned");
   ABX_REQUIRE((long long)B * S <= 65535, "abx_pair_attention: B*S exceeds 65535");
   cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 0 && D % 16 == 0 && tc5_smem_bytes(L, D) <= 113 * 1024 && (gate == nullptr || (uintptr_t)gate % 16 == 0)) {
+    switch (D) {
+      case 16: return launch_attention_tc5<16>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
+      case 32: return launch_attention_tc5<32>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
+      case 48: return launch_attention_tc5<48>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
+    }
+  }
   switch (D) {
     case 16: return launch_attention_mma<16>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
     case 32: return launch_attention_mma<32>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);

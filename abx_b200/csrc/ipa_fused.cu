@@ -689,8 +689,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     RoleProf rp_; if constexpr (kProf) rp_.start();
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1, pb = c % kPD, j0 = c * kChunk;
-      ABX_WAIT(0, kv_full + buf, (c >> 1) & 1, 601);
-      ABX_WAIT(1, p_empty + pb, ((c / kPD) & 1) ^ 1, 602);
+      ABX_WAIT_SPIN(0, kv_full + buf, (c >> 1) & 1, 601);
+      ABX_WAIT_SPIN(1, p_empty + pb, ((c / kPD) & 1) ^ 1, 602);
       if (t == 0) resc[(c + 2) & 3] = 0u;
       const float* kvp = KVs + (size_t)buf * kChunk * kKVRow + h * kQK;
       const float* bs0 = BSs + ((size_t)buf * kMaxRows + r0) * kBiasRow + h;
@@ -788,8 +788,8 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
     RoleProf rp_; if constexpr (kProf) rp_.start();
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1, pb = c % kPD, nk = min(kChunk, N - c * kChunk);
-      ABX_WAIT(0, kv_full + buf, (c >> 1) & 1, 701);
-      ABX_WAIT(1, p_full + pb, (c / kPD) & 1, 702);
+      ABX_WAIT_SPIN(0, kv_full + buf, (c >> 1) & 1, 701);
+      ABX_WAIT_SPIN(1, p_full + pb, (c / kPD) & 1, 702);
 #pragma unroll
       for (int g = 0; g < 2; ++g) {                  // rows 10 g .. 10 g + 9 live at [12 g, 12 g + 10) of a 24-float row
         const float4* ap = reinterpret_cast<const float4*>(AL + ((size_t)pb * kH + h) * kPfRow + g * 12);

@@ -64,7 +64,7 @@ def pair_attention(qkv, bias, key_mask, num_head, impl='mma', gated=False):
     """Fused attention core for TriangleAttention.  qkv [B,S,L,3*H*D] (q | k | v slices of one projection;
     with `gated=True` [B,S,L,4*H*D] = q | k | v | gate pre-activation), bias [B,H,L,L], key_mask [B,L]
     (bool/float, None = keep all)  ->  [B,S,L,H*D] (times sigmoid(gate) when gated).
-    impl: 'mma' (tensor cores, 3xTF32) or 'simt'."""
+    impl: 'mma' (mma.sync 3xTF32, default), 'tc5' (tcgen05 3xTF32) or 'simt'."""
     L_ = lib.load()
     B, S, L, Cw = qkv.shape
     HD = Cw // (4 if gated else 3)
@@ -75,7 +75,7 @@ def pair_attention(qkv, bias, key_mask, num_head, impl='mma', gated=False):
     out = torch.empty(B, S, L, HD, device=qkv.device, dtype=torch.float32)
     base, esz = qkv.data_ptr(), 4
     with lib.device_guard(qkv):
-        lib.check(L_.abx_pair_attention_impl(lib.stream(), {'mma': 0, 'simt': 1}[impl], B, S, L, num_head, D, base,
+        lib.check(L_.abx_pair_attention_impl(lib.stream(), {'tc5': 0, 'simt': 1, 'mma': 2}[impl], B, S, L, num_head, D, base,
                                              base + HD * esz, base + 2 * HD * esz, Cw,
                                              lib.ptr(bias), lib.ptr(km), (base + 3 * HD * esz) if gated else None, lib.ptr(out)))
     return out

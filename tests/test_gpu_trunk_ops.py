@@ -41,7 +41,7 @@ def _attention_reference(qkv, bias, key_mask, H):
     return torch.einsum('bshqk,bshkd->bsqhd', w, v).reshape(B, S, L, H * D)
 
 
-@pytest.mark.parametrize('impl', ['mma', 'simt'])
+@pytest.mark.parametrize('impl', ['tc5', 'mma', 'simt'])
 @pytest.mark.parametrize('B,S,L,H,D', [(1, 3, 37, 4, 48), (2, 5, 350, 4, 48), (1, 2, 400, 2, 32), (1, 1, 1, 1, 16), (1, 2, 65, 3, 64),
                                        (1, 2, 351, 4, 48)])
 def test_pair_attention_matches_reference(cuda_device, B, S, L, H, D, impl):
@@ -67,7 +67,7 @@ def test_pair_attention_all_keys_masked_is_uniform(cuda_device):
     bias = np_randn(13, 1, 4, 40, 40).cuda()
     mask = torch.zeros(1, 40, dtype=torch.bool).cuda()
     ref = _attention_reference(qkv, bias, mask, 4)
-    for impl in ('mma', 'simt'):
+    for impl in ('tc5', 'mma', 'simt'):
         out = ops.pair_attention(qkv, bias, mask, 4, impl=impl)
         assert torch.isfinite(out).all()
         assert maxabs(out.cpu(), ref.cpu()) < 3e-6

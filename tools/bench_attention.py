@@ -2,13 +2,13 @@
 import json, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from abx_b200 import ops
-B, S, L, H, D = 4, 350, 350, 4, 48
+B, S, L, H, D = 8, 350, 350, 4, 48
 g = torch.Generator(device='cuda').manual_seed(0)
 qkv = torch.randn(B, S, L, 3 * H * D, device='cuda', generator=g)
 bias = torch.randn(B, H, L, L, device='cuda', generator=g)
 mask = torch.ones(B, L, device='cuda', dtype=torch.bool)
 ref = None
-for impl in ('simt', 'mma'):
+for impl in ('tc5', 'mma'):
     for _ in range(2):
         out = ops.pair_attention(qkv, bias, mask, H, impl=impl)
     torch.cuda.synchronize()

@@ -1,2 +1,2 @@
-timeout 150 python tools/ipa_debug.py 2,37 8,350 2>&1 | grep "B=\|FAILED\|rror" | cut -c1-120
-timeout 120 python tools/bench_ipa.py --B 8 --N 350 --profile 1 --prof 1 --graph 8 > gpurun_out/bench_ipa_fused_B8_q36.log 2>&1; grep "loop\|extra\|ipa_fused_kernel\|ms_per_layer\|rror" gpurun_out/bench_ipa_fused_B8_q36.log | cut -c1-330
+timeout 300 python -m pytest tests/test_gpu_trunk_ops.py -q -x -k "pair_attention" 2>&1 | tail -3
+timeout 120 python tools/bench_attention.py 2>&1 | tail -3
