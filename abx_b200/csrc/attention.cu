@@ -359,14 +359,18 @@ namespace abx {
 template <int D>
 int launch_attention_tc5(cudaStream_t st, int B, int S, int L, int H, const float* q, const float* k, const float* v, int ld,
                          const float* bias, const float* key_mask, const float* gate, float* out);
-// shared memory of the tcgen05 kernel (attention_tc5.cu): Q, K tile and V^T tile as hi / lo operand tiles + the key mask
-static size_t tc5_smem_bytes(int L, int D) {
-  const size_t q = (size_t)(D / 4) * (128 * 16 + 16), k = (size_t)(D / 4) * (64 * 16 + 16), v = (size_t)16 * (D * 16 + 16);
-  return 2 * (q + k + v) + (size_t)((L + 63) / 64) * 64 * 4 + 64;
+template <int D> size_t attention_tc5_smem(int L);   // shared memory of the tcgen05 kernel (attention_tc5.cu) for key length L
+static bool tc5_fits(int L, int D) {
+  switch (D) {
+    case 16: return attention_tc5_smem<16>(L) <= 227 * 1024;
+    case 32: return attention_tc5_smem<32>(L) <= 227 * 1024;
+    case 48: return attention_tc5_smem<48>(L) <= 227 * 1024;
+  }
+  return false;                                      // D = 64: the operand tiles of two query slots do not fit
 }
 }  // namespace abx
 
-// impl: 0 = tcgen05 kernel (attention_tc5.cu; falls back to 2 when its operand tiles do not fit 113 KB, i.e. D = 64),
+// impl: 0 = tcgen05 kernel (attention_tc5.cu; falls back to 2 when its operand tiles do not fit shared memory, i.e. D = 64),
 //       1 = SIMT kernel, 2 = mma.sync kernel
 extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, int D, const float* q, const float* k,
                                        const float* v, int ld, const float* bias, const float* key_mask, const float* gate,
@@ -383,7 +387,7 @@ extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int
               "abx_pair_attention: q, k, v, out must be 16-byte aligned");
   ABX_REQUIRE((long long)B * S <= 65535, "abx_pair_attention: B*S exceeds 65535");
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 0 && D % 16 == 0 && tc5_smem_bytes(L, D) <= 113 * 1024 && (gate == nullptr || (uintptr_t)gate % 16 == 0)) {
+  if (impl == 0 && tc5_fits(L, D) && (gate == nullptr || (uintptr_t)gate % 16 == 0)) {
     switch (D) {
       case 16: return launch_attention_tc5<16>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
       case 32: return launch_attention_tc5<32>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);

@@ -11,10 +11,14 @@
 // (register budgets re-balanced with setmaxnreg):
 //   WG0  warp 0: TMA producer — cp.async.bulk.tensor (128-byte swizzle) of the raw fp32 A / W k-slabs
 //                (128 x 32 and BN x 32 elements) into a shared-memory ring
-//        warp 1: allocates TMEM; one lane issues 3 x 4 tcgen05.mma.kind::tf32 per slab into one of two TMEM
-//                partial-sum buffers and commits to the slab's `empty` and the buffer's `acc_ready` barriers
-//   WG1  converters: write the lo tile of each landed slab (the tensor core ignores the 13 low mantissa bits
-//        of a tf32 operand, so the raw tile already is the hi part), fence generic->async proxy, arrive `conv`
+//        warp 1: allocates TMEM; one lane issues 3 x 4 tcgen05.mma.kind::tf32 per slab — A FROM TENSOR MEMORY
+//                (TS mode), W from shared memory — into a ring of TMEM partial-sum buffers and commits to the
+//                slab's `empty` and the buffer's `acc_ready` barriers
+//   WG1  converters: thread = row of the landed A slab: reads its 32 floats from the swizzled tile, splits
+//        hi / lo and writes both with tcgen05.st into the slab's stage of the TMEM A ring (the A operand never
+//        goes back to shared memory: the SS-mode loop sat on the shared-memory port, 192 KB per slab against
+//        128 KB now); then writes the lo tile of W (the tensor core ignores the 13 low mantissa bits of a tf32
+//        operand, so the raw W tile already is its hi part), fence generic->async proxy, arrive `conv`
 //   WG2, WG3  accumulator warpgroups, alternating tiles (ping-pong): per slab read the partial sum with
 //        tcgen05.ld (warp w owns TMEM lanes 32 (w%4)..) and add it to register accumulators with
 //        round-to-nearest — the tensor core itself accumulates with truncation, which over K/8 chained steps
@@ -35,18 +39,24 @@ namespace {
 // k-slab width: 32 fp32 = one 128-byte swizzle row, or 16 fp32 = one 64-byte swizzle row (twice the pipeline depth
 // in the same shared memory: the TMA -> convert -> MMA -> commit round trip, not bandwidth, paces the main loop)
 constexpr int kBM = 128, kBK = ABX_GEMM_BK;
-static_assert(kBK == 32 || kBK == 16, "k-slab must be 16 or 32 floats");
-constexpr int kDrainDefault = 32 / kBK;         // register accumulation once per 32 columns of K by default
+static_assert(kBK == 32, "k-slab = one 128-byte swizzle row (the converter reads the A tile row by row)");
+constexpr int kDrainDefault = 2;                // k-slabs per TMEM partial sum (register accumulation once per 64 columns of K)
 constexpr int kThreads = 512, kConvThreads = 128, kAccThreads = 128;
-constexpr int kRegsCtl = 40, kRegsConv = 72, kRegsAcc = 184;   // 128*(40+72) + 256*184 <= 65536
+constexpr int kRegsCtl = 48, kRegsConv = 72, kRegsAcc = 192;   // 128*(48+72) + 256*192 = 65536 - 1024
 constexpr uint32_t kTileABytes = kBM * kBK * 4;
+static_assert(kBM == kConvThreads, "converter thread = A row = tensor-memory lane");
 
 template <int BN> struct GemmCfg {
   static constexpr uint32_t kTileBBytes = BN * kBK * 4;
-  static constexpr uint32_t kStageBytes = 2 * (kTileABytes + kTileBBytes);     // raw/hi + lo for A and B
-  static constexpr int kStages = (BN >= 128 ? 3 : (BN >= 64 ? 4 : 5)) * (32 / kBK);
-  static constexpr uint32_t kTmemCols = 4 * BN;                                // two partial-sum buffers per accumulator WG
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 512 /* barriers */;
+  static constexpr uint32_t kStageBytes = kTileABytes + 2 * kTileBBytes;       // raw A (staging only), raw W (= hi), W lo
+  static constexpr int kStages = 4 * (32 / kBK);                               // = stages of the TMEM A ring
+  static constexpr int kAccBufs = BN >= 128 ? 2 : 4;                           // ring of TMEM partial-sum buffers
+  static constexpr uint32_t kAColBase = kAccBufs * BN;                         // A ring: stage s at columns kAColBase + 2 kBK s (hi | lo)
+  static constexpr uint32_t kTmemCols = 512;
+  static_assert(kAColBase + kStages * 2 * kBK <= kTmemCols, "tensor memory budget");
+  static constexpr uint32_t kStagingBytes = 8 * 4096;                          // epilogue: 32 rows x 32 columns per accumulator warp
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 512 /* barriers */ + kStagingBytes;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,15 +70,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// A wait that cannot hang the device: a synchronisation bug ends the kernel with a trap (launch error) after ~1 s.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
+  uint32_t ok = 0, tries = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok && ++tries > (1u << 24)) __trap();
   } while (!ok);
 }
 
@@ -103,6 +115,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (128 lanes x 8 columns per k-step), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -119,6 +145,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// Per-role wait / work cycle counters of CTA 0 (ABX_GEMM_PROF=1; read with abx_gemm_profile): what the roles wait for.
+// Compiled in only with -DABX_GEMM_PROFILE=1 (ABX_GEMM_PROFILE=1 python -m abx_b200.build): the counters cost registers.
+#ifndef ABX_GEMM_PROFILE
+#define ABX_GEMM_PROFILE 0
+#endif
+__device__ unsigned long long g_gemm_prof[32];
+#define ABX_GEMM_PWAIT(slot, bar, par)                                                  \
+  do {                                                                                  \
+    if (prof) { const long long t0__ = clock64(); mbar_wait(bar, par); pw[slot] += clock64() - t0__; } \
+    else mbar_wait(bar, par);                                                           \
+  } while (0)
 
 struct Epilogue {
   const float* bias;       // [Nout] or null
@@ -203,6 +241,59 @@ __device__ __forceinline__ void store_row(const float (&acc)[BN], const Epilogue
   }
 }
 
+// Coalesced epilogue of one warp's 32 rows (lane = row holds acc[0..BN) = columns n0..): 32 columns at a time go through a
+// 4 KB per-warp staging tile (16-byte pieces XOR-swizzled by the row: both directions at the 4-wavefront minimum), then lane
+// (row 4 i + lane / 8, piece lane % 8) loads gate / residual and stores y as whole 128-byte row segments — a warp-level store
+// touches 4 lines instead of 32 half-used sectors (the row-per-lane stores of store_row kept the LSU busy ~10k clk per tile and
+// slowed the other warpgroup's tensor-memory reads down with them).  Requires Nout % 32 == 0, 16-byte aligned operands, no transpose.
+template <int ACT, int BN>
+__device__ __forceinline__ void store_tile_coalesced(const float (&acc)[BN], const Epilogue& ep, float* __restrict__ y, int ldy,
+                                                     int row_base, int n0, int Nout, int M, uint8_t* stg, int lane) {
+  const int my_row = row_base + lane;
+  const float sc_own = (ep.row_scale && my_row < M) ? __ldg(ep.row_scale + my_row) : 1.f;
+  const int rsub = lane >> 3, c4 = lane & 7;
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (n0 + c0 >= Nout) break;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      *reinterpret_cast<float4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) =
+          make_float4(acc[c0 + 4 * u], acc[c0 + 4 * u + 1], acc[c0 + 4 * u + 2], acc[c0 + 4 * u + 3]);
+    __syncwarp();
+    const int col = n0 + c0 + 4 * c4;
+    const float4 bv = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ib = 0; ib < 8; ib += 4) {               // 4 row steps at a time: their gate / residual loads are in flight together
+      float4 g[4], r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = row_base + 4 * (ib + i) + rsub;
+        g[i] = r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < M) {
+          const size_t o = (size_t)row * ldy + col;
+          if (ACT == 2 || ACT == 4) g[i] = *reinterpret_cast<const float4*>(ep.gate + o);
+          if (ep.residual) r[i] = *reinterpret_cast<const float4*>(ep.residual + o);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = 4 * (ib + i) + rsub, row = row_base + rl;
+        const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+        const float sc = __shfl_sync(0xffffffffu, sc_own, rl);
+        if (row < M) {
+          float4 v;
+          v.x = epilogue_op<ACT>(a.x, bv.x, g[i].x, sc, r[i].x);
+          v.y = epilogue_op<ACT>(a.y, bv.y, g[i].y, sc, r[i].y);
+          v.z = epilogue_op<ACT>(a.z, bv.z, g[i].z, sc, r[i].z);
+          v.w = epilogue_op<ACT>(a.w, bv.w, g[i].w, sc, r[i].w);
+          *reinterpret_cast<float4*>(y + (size_t)row * ldy + col) = v;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // GLU epilogue (act 5): the tile's first BN/2 accumulator columns are projections, the last BN/2 their gates:
 //   y[row, n0/2 + c] = (acc[c] + b[n0+c]) * sigmoid(acc[BN/2+c] + b[n0+BN/2+c]) * row_scale[row]
 // (left/right projections and gates of TriangleMultiplication, seqformer.py:452-460, as one GEMM with the weight
@@ -250,16 +341,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   auto stage_a = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
-  auto stage_alo = [&](int s) { return stage_a(s) + kTileABytes; };
-  auto stage_b = [&](int s) { return stage_a(s) + 2 * kTileABytes; };
+  auto stage_b = [&](int s) { return stage_a(s) + kTileABytes; };
   auto stage_blo = [&](int s) { return stage_b(s) + Cfg::kTileBBytes; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * Cfg::kStageBytes);
   uint64_t* full = bars;                        // TMA -> converters
   uint64_t* conv = bars + kStages;              // converters -> MMA
   uint64_t* empty = bars + 2 * kStages;         // MMA -> TMA
-  uint64_t* acc_ready = bars + 3 * kStages;     // [2 WGs][2] MMA -> accumulator WG (partial sum of one k-slab in TMEM)
-  uint64_t* acc_free = bars + 3 * kStages + 4;  // [2 WGs][2] accumulator WG -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 8);
+  // The TMEM partial-sum buffers form one ring shared by both accumulator warpgroups, but every (warpgroup, buffer) pair
+  // has its own barriers: an mbarrier wait only carries a parity, so each barrier must be waited on use after use by a
+  // single party (a warpgroup that skipped the other one's uses would pass on a stale phase).
+  uint64_t* acc_ready = bars + 3 * kStages;     // [2 WGs][4] MMA -> accumulator WG (partial sum of one k-slab in TMEM)
+  uint64_t* acc_free = bars + 3 * kStages + 8;  // [2 WGs][4] accumulator WG -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // split-K: tile = (split, m block, n block); split s covers k-slabs [s kbs, min((s+1) kbs, total)) and writes its
@@ -280,7 +373,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(conv + s, kConvThreads / 32);      // one arrival per converter warp
       mbar_init(empty + s, 1);
     }
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 8; ++b) {
       mbar_init(acc_ready + b, 1);
       mbar_init(acc_free + b, kAccThreads / 32);   // one arrival per accumulator warp
     }
@@ -295,6 +388,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const bool prof = ABX_GEMM_PROFILE && (trust_trunc & 32) && blockIdx.x == 0;
   // programmatic dependent launch: the set-up above overlaps the tail of the previous kernel in the stream; nothing
   // it wrote is touched before this point (no-ops for an ordinary launch)
   griddep_wait();
@@ -309,6 +403,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (warp == 0 && lane == 0) {
       // ---------------- TMA producer ----------------
       uint32_t it = 0;
+      unsigned long long pw[2] = {0, 0};
+      const long long tstart = clock64();
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int rem = tile % mnt, kb0 = (tile / mnt) * kbs, nkb = tile_nkb(tile);
         int m0 = ((rem / nt) % mt) * kBM, n0 = (rem % nt) * BN;
@@ -316,50 +412,113 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(empty + s, ph ^ 1);
+          ABX_GEMM_PWAIT(0, empty + s, ph ^ 1);
           if (trust_trunc & 16) { mbar_arrive(full + s); continue; }      // timing probe: no TMA at all
           mbar_expect_tx(full + s, kTileABytes + Cfg::kTileBBytes);
           tma_load_2d(stage_a(s), &map_a, full + s, (kb0 + kb) * kBK, m0);
           tma_load_2d(stage_b(s), &map_b, full + s, (kb0 + kb) * kBK, n0);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------- MMA issuer ----------------
+      if (prof) { g_gemm_prof[0] = pw[0]; g_gemm_prof[1] = clock64() - tstart; g_gemm_prof[2] = it; }
+    } else if ((warp == 1 || warp == 2) && lane == 0) {
+      // ---------------- MMA issuers (two threads, alternating partial sums) ----------------
+      // One thread cannot keep the tensor pipe fed: a 12-MMA slab (~1.1k clk of pipe time at the measured tf32 rate) blocks
+      // the issuing thread for about as long (the MMA queue is shallow), and only then can it run the barrier waits of the next
+      // slab (~200 clk each even when already complete) while the pipe drains.  Two threads issue alternate partial sums —
+      // disjoint TMEM buffers and smem / TMEM-A stages, and tcgen05.commit tracks the issuing thread's own MMAs — so one
+      // thread's waits overlap the other's MMAs.
       constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+      const uint32_t X = warp - 1;                    // this thread issues the partial sums with (index & 1) == X
       // Partial sums: `kb_per_drain` consecutive k-slabs are chained in one TMEM buffer (the first MMA of a group
       // overwrites), then handed to the accumulator WG, which adds them up in registers with round-to-nearest.
-      uint32_t it = 0, lit[2] = {0, 0};               // lit[g]: partial sums issued so far for accumulator WG g
+      uint32_t it = 0, pit = 0;                       // k-slabs / partial sums so far (ring of kAccBufs TMEM buffers)
+      uint32_t used = 0, owner = 0, fpar = 0;         // per buffer: holds a partial / warpgroup of its last partial;
+                                                      // fpar bit 4 g + b: parity of the next acc_free[g][b] completion
       int j = 0;
+      unsigned long long pw[3] = {0, 0, 0};
+      const long long tstart = clock64();
+      auto a_addr = [&](int s) { return tmem_base + Cfg::kAColBase + (uint32_t)s * 2 * kBK; };
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
-        const int g = j & 1;
+        const uint32_t g = j & 1;
         const int nkb = tile_nkb(tile);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          const uint32_t buf = 2 * g + (lit[g] & 1), use = lit[g] >> 1;
-          const bool first = (kb % kb_per_drain) == 0, last = ((kb + 1) % kb_per_drain) == 0 || kb + 1 == nkb;
-          if (first) mbar_wait(acc_free + buf, (use & 1) ^ 1);
-          mbar_wait(conv + s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb0 = 0; kb0 < nkb; kb0 += kb_per_drain, ++pit) {
+          const int cnt = min(kb_per_drain, nkb - kb0);
+          const uint32_t it0 = it;
+          it += cnt;
+          if ((pit & 1) != X) continue;
+          const uint32_t buf = pit % Cfg::kAccBufs;
+          if ((used >> buf) & 1) {                    // the buffer's previous partial must have been drained by its owner
+            const uint32_t idx = 4 * ((owner >> buf) & 1) + buf;
+            ABX_GEMM_PWAIT(0, acc_free + idx, (fpar >> idx) & 1);
+            fpar ^= 1u << idx;
+          }
+          used |= 1u << buf;
+          owner = (owner & ~(1u << buf)) | (g << buf);
           const uint32_t tmem_acc = tmem_base + buf * BN;
-          const uint64_t a_hi = umma_desc_sw128(smem_u32(stage_a(s))), a_lo = umma_desc_sw128(smem_u32(stage_alo(s)));
-          const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_b(s))), b_lo = umma_desc_sw128(smem_u32(stage_blo(s)));
-          // small cross terms first, then the hi*hi terms (UMMA_K = 8 tf32 = 32 bytes: +2 in the addr>>4 field)
-          if (!(trust_trunc & 4)) {
+          if (cnt == 2) {
+            // two slabs per partial: every small cross term (hi*lo, lo*hi) of both slabs first, then the hi*hi terms — the
+            // tensor core truncates when it adds into the accumulator, and the number of additions made at full magnitude
+            // (4 per slab) stays what it is with one slab per partial
+            const int s0 = it0 % kStages, s1 = (it0 + 1) % kStages;
+            ABX_GEMM_PWAIT(1, conv + s0, (it0 / kStages) & 1);
+            ABX_GEMM_PWAIT(1, conv + s1, ((it0 + 1) / kStages) & 1);
+            const long long tissue = prof ? clock64() : 0;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (!(trust_trunc & 4)) {
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {
-            umma_tf32(tmem_acc, a_hi + 2 * k, b_lo + 2 * k, idesc, (k != 0 || !first) ? 1u : 0u);
-            umma_tf32(tmem_acc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
-          }
+              for (int u = 0; u < 2; ++u) {
+                const int s = u ? s1 : s0;
+                const uint32_t a_hi = a_addr(s), a_lo = a_hi + kBK;
+                const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_b(s))), b_lo = umma_desc_sw128(smem_u32(stage_blo(s)));
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) umma_tf32(tmem_acc, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
-          }
-          umma_commit(empty + s);                    // slab free once these MMAs have read it
-          if (last) {
-            umma_commit(acc_ready + buf);            // partial sum complete
-            ++lit[g];
+                for (int k = 0; k < kBK / 8; ++k) {
+                  umma_tf32_ts(tmem_acc, a_hi + 8 * k, b_lo + 2 * k, idesc, (u != 0 || k != 0) ? 1u : 0u);
+                  umma_tf32_ts(tmem_acc, a_lo + 8 * k, b_hi + 2 * k, idesc, 1);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int s = u ? s1 : s0;
+                const uint32_t a_hi = a_addr(s);
+                const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_b(s)));
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) umma_tf32_ts(tmem_acc, a_hi + 8 * k, b_hi + 2 * k, idesc, 1);
+                umma_commit(empty + s);               // smem slab and TMEM A stage free once the MMAs so far have read them
+              }
+            } else {
+              umma_commit(empty + s0);
+              umma_commit(empty + s1);
+            }
+            umma_commit(acc_ready + 4 * g + buf);     // partial sum complete
+            if (prof) pw[2] += clock64() - tissue;
+          } else {
+            for (int u = 0; u < cnt; ++u) {           // any other group size: slab by slab (small cross terms first, then hi*hi)
+              const uint32_t iu = it0 + u;
+              const int s = iu % kStages;
+              ABX_GEMM_PWAIT(1, conv + s, (iu / kStages) & 1);
+              const long long tissue = prof ? clock64() : 0;
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t a_hi = a_addr(s), a_lo = a_hi + kBK;
+              const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_b(s))), b_lo = umma_desc_sw128(smem_u32(stage_blo(s)));
+              if (!(trust_trunc & 4)) {
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) {
+                  umma_tf32_ts(tmem_acc, a_hi + 8 * k, b_lo + 2 * k, idesc, (u != 0 || k != 0) ? 1u : 0u);
+                  umma_tf32_ts(tmem_acc, a_lo + 8 * k, b_hi + 2 * k, idesc, 1);
+                }
+#pragma unroll
+                for (int k = 0; k < kBK / 8; ++k) umma_tf32_ts(tmem_acc, a_hi + 8 * k, b_hi + 2 * k, idesc, 1);
+              }
+              umma_commit(empty + s);
+              if (u + 1 == cnt) umma_commit(acc_ready + 4 * g + buf);
+              if (prof) pw[2] += clock64() - tissue;
+            }
           }
         }
+      }
+      if (prof) {
+        unsigned long long* o = g_gemm_prof + (X ? 20 : 4);
+        o[0] = pw[0]; o[1] = pw[1]; o[2] = clock64() - tstart; o[3] = pw[2];
       }
     }
   } else if (wg == 1) {
@@ -367,36 +526,60 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConv));
     const int ct = threadIdx.x - 128;                // 0..127
     uint32_t it = 0;
+    unsigned long long pw[1] = {0};
+    const long long tstart = clock64();
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int nkb = tile_nkb(tile);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(full + s, ph);
-        if (trust_trunc & 2) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); __syncwarp(); if (lane == 0) mbar_arrive(conv + s); continue; }
-        auto split = [&](float4* hi_p, float4* lo_p, int i) {
-          float4 v = hi_p[i], h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          if (!(trust_trunc & 1)) hi_p[i] = h;
-          lo_p[i] = l;
-        };
-        float4* a = reinterpret_cast<float4*>(stage_a(s));
-        float4* alo = reinterpret_cast<float4*>(stage_alo(s));
+        ABX_GEMM_PWAIT(0, full + s, ph);
+        if (trust_trunc & 2) { __syncwarp(); if (lane == 0) mbar_arrive(conv + s); continue; }   // timing probe: no conversion
+        // A: thread = row ct of the 128-byte-swizzled tile (16-byte chunk c of row r sits at chunk c ^ (r & 7)); the stage's
+        // TMEM columns are free: `full` was armed only after the MMAs of the stage's previous use had committed `empty`
+        {
+          const uint8_t* arow = stage_a(s) + ct * 128;
+          const uint32_t ta = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + Cfg::kAColBase + (uint32_t)s * 2 * kBK;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(arow + (((4 * half + c) ^ (ct & 7)) << 4));
+              const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                hi[4 * c + u] = __float_as_uint(x[u]) & 0xffffe000u;
+                lo[4 * c + u] = __float_as_uint(x[u] - __uint_as_float(hi[4 * c + u]));
+              }
+            }
+            tmem_st16(ta + 16 * half, hi);
+            tmem_st16(ta + kBK + 16 * half, lo);
+          }
+        }
+        // W: lo tile next to the raw tile (element-wise, layout preserved)
+        {
+          const float4* b = reinterpret_cast<const float4*>(stage_b(s));
+          float4* blo = reinterpret_cast<float4*>(stage_blo(s));
 #pragma unroll 8
-        for (int i = ct; i < (int)(kTileABytes / 16); i += kConvThreads) split(a, alo, i);
-        float4* b = reinterpret_cast<float4*>(stage_b(s));
-        float4* blo = reinterpret_cast<float4*>(stage_blo(s));
-#pragma unroll 8
-        for (int i = ct; i < (int)(Cfg::kTileBBytes / 16); i += kConvThreads) split(b, blo, i);
+          for (int i = ct; i < (int)(Cfg::kTileBBytes / 16); i += kConvThreads) {
+            const float4 v = b[i];
+            float4 l;
+            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            blo[i] = l;
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();                               // every lane's lo-tile writes are fenced before the warp's single arrival
         if (lane == 0) mbar_arrive(conv + s);
       }
     }
+    if (prof && ct == 0) { g_gemm_prof[8] = pw[0]; g_gemm_prof[9] = clock64() - tstart; }
   } else {
     // ---------------- accumulator / epilogue warpgroups (ping-pong on tiles): lane = one output row ----------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsAcc));
@@ -406,8 +589,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
                         (!ep.residual || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) &&
                         (!ep.gate || (reinterpret_cast<uintptr_t>(ep.gate) & 15) == 0);
-    uint32_t lit = 0;                                // k-slabs this WG has drained (its own phase counter)
+    // position of a tile's first partial sum in the shared ring = partial sums of all earlier tiles of this CTA
+    auto ring_pos = [&](int tile) -> uint32_t {
+      const int j = (tile - (int)blockIdx.x) / (int)gridDim.x;
+      if (splits == 1) return (uint32_t)(j * ((nkb_total + kb_per_drain - 1) / kb_per_drain));
+      uint32_t p = 0;
+      for (int t2 = blockIdx.x; t2 < tile; t2 += gridDim.x) p += (tile_nkb(t2) + kb_per_drain - 1) / kb_per_drain;
+      return p;
+    };
+    uint32_t rpar = 0;                               // bit b: parity of the next acc_ready[g][b] completion
+    unsigned long long pw[3] = {0, 0, 0};
+    const long long tstart = clock64();
     for (int tile = blockIdx.x + g * gridDim.x; tile < tiles; tile += 2 * gridDim.x) {
+      uint32_t pit = ring_pos(tile);
       const int rem = tile % mnt, nkb = tile_nkb(tile);
       const int m0 = ((rem / nt) % mt) * kBM, n0 = (rem % nt) * BN;
       float* __restrict__ yt = y + (long long)(tile / mnt) * split_stride +
@@ -424,9 +618,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
       for (int c = 0; c < BN; ++c) acc[c] = 0.f;
       const int ngroups = (nkb + kb_per_drain - 1) / kb_per_drain;
-      for (int gi = 0; gi < ngroups; ++gi, ++lit) {
-        const uint32_t buf = 2 * g + (lit & 1), use = lit >> 1;
-        mbar_wait(acc_ready + buf, use & 1);
+      for (int gi = 0; gi < ngroups; ++gi, ++pit) {
+        const uint32_t buf = pit % Cfg::kAccBufs;
+        ABX_GEMM_PWAIT(0, acc_ready + 4 * g + buf, (rpar >> buf) & 1);
+        rpar ^= 1u << buf;
+        const long long tdrain = prof ? clock64() : 0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -438,9 +634,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_free + buf);
+        if (lane == 0) mbar_arrive(acc_free + 4 * g + buf);
+        if (prof) pw[1] += clock64() - tdrain;
       }
-      if (row < M) {
+      const long long tepi = prof ? clock64() : 0;
+      if (vec_ok && ep.transpose_n == 0 && ep.act != 5 && Nout % 32 == 0) {
+        uint8_t* stg = smem + (size_t)kStages * Cfg::kStageBytes + 512 + (size_t)(4 * g + q) * 4096;
+        const int rb = m0 + 32 * q;
+        switch (ep.act) {
+          case 0: store_tile_coalesced<0, BN>(acc, ep, yt, ldy, rb, n0, Nout, M, stg, lane); break;
+          case 1: store_tile_coalesced<1, BN>(acc, ep, yt, ldy, rb, n0, Nout, M, stg, lane); break;
+          case 2: store_tile_coalesced<2, BN>(acc, ep, yt, ldy, rb, n0, Nout, M, stg, lane); break;
+          case 3: store_tile_coalesced<3, BN>(acc, ep, yt, ldy, rb, n0, Nout, M, stg, lane); break;
+          default: store_tile_coalesced<4, BN>(acc, ep, yt, ldy, rb, n0, Nout, M, stg, lane); break;
+        }
+      } else if (row < M) {
         switch (ep.act) {
           case 0: store_row<0, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
           case 1: store_row<1, BN>(acc, ep, yt, ldy, row, n0, Nout, vec_ok); break;
@@ -450,6 +658,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           default: if constexpr (BN == 128) store_row_glu<BN>(acc, ep, yt, ldy, row, n0, Nout); break;
         }
       }
+      if (prof) pw[2] += clock64() - tepi;
+    }
+    if (prof && (threadIdx.x & 127) == 0) {
+      unsigned long long* o = g_gemm_prof + 12 + 4 * g;
+      o[0] = pw[0]; o[1] = pw[1]; o[2] = pw[2]; o[3] = clock64() - tstart;
     }
   }
 
@@ -511,7 +724,8 @@ int trust_trunc() {
   static int v = [] {
     const char* e = getenv("ABX_GEMM_TRUST_TRUNC");
     const char* d = getenv("ABX_GEMM_DEBUG_SKIP");      // timing experiments only: 2 skip split, 4 skip MMA, 8 skip drain, 16 skip TMA
-    return ((e && e[0] == '0') ? 0 : 1) | (d ? (atoi(d) & 30) : 0);
+    const char* pf = getenv("ABX_GEMM_PROF");           // per-role cycle counters of CTA 0 (abx_gemm_profile)
+    return ((e && e[0] == '0') ? 0 : 1) | (d ? (atoi(d) & 30) : 0) | ((pf && pf[0] == '1') ? 32 : 0);
   }();
   return v;
 }
@@ -607,6 +821,16 @@ int launch_gemm_tf32x3_batched_nt(cudaStream_t s, int batches, int n, int kpad, 
 }
 
 }  // namespace abx
+
+// Diagnostics: copies the 32 per-role cycle counters the last ABX_GEMM_PROF=1 launch recorded for CTA 0
+// ([0] TMA wait-empty, [1] TMA total, [2] k-slabs; [4] issuer wait-acc_free, [5] wait-conv, [6] total, [7] issue;
+//  [8] converter wait-full, [9] total; [12 + 4 g ..] accumulator WG g: wait-ready, drain, epilogue, total).
+extern "C" int abx_gemm_profile(unsigned long long* out32) {
+  ABX_REQUIRE(out32 != nullptr, "abx_gemm_profile: null output");
+  ABX_CUDA(cudaDeviceSynchronize());
+  ABX_CUDA(cudaMemcpyFromSymbol(out32, abx::g_gemm_prof, 32 * sizeof(unsigned long long)));
+  return ABX_OK;
+}
 
 extern "C" int abx_gemm_tf32x3_batched_nt(void* stream, int batches, int n, int kpad, int inner, int outer_rows, int total_rows,
                                           const float* a, const float* b, float* out, int ldo) {

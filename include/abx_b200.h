@@ -188,6 +188,10 @@ int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, 
  * 1 SIMT (abx_linear_f32), 2 tcgen05 only.  Process-wide; meant for A/B measurements and tests. */
 int abx_set_gemm_backend(int backend);
 
+/* Diagnostics of abx_gemm_tf32x3 (no reference counterpart): with ABX_GEMM_PROF=1 in the environment CTA 0 of every
+ * launch records per-role wait / work cycle counters; this copies the 32 counters of the last launch (host buffer). */
+int abx_gemm_profile(unsigned long long* out32);
+
 /* ---- Invariant Point Attention ---------------------------------------------------------------- */
 /* Weights of abx.model.folding.InvariantPointAttention (folding.py:23-45), reference state_dict
  * layout (out_features x in_features, row-major). */
