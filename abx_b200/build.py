@@ -15,7 +15,8 @@ LIB = os.path.join(CSRC, 'libabx_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
          '-Xptxas', '-v', '-I', INCLUDE, '-I', CSRC] + \
-        ([f'-DABX_GEMM_PROFILE={os.environ["ABX_GEMM_PROFILE"]}'] if os.environ.get('ABX_GEMM_PROFILE') else [])
+        ([f'-DABX_GEMM_PROFILE={os.environ["ABX_GEMM_PROFILE"]}'] if os.environ.get('ABX_GEMM_PROFILE') else []) + \
+        ([f'-DABX_ATTN_PROFILE={os.environ["ABX_ATTN_PROFILE"]}'] if os.environ.get('ABX_ATTN_PROFILE') else [])
 
 
 def sources():

@@ -358,7 +358,7 @@ static int launch_attention_mma(cudaStream_t st, int B, int S, int L, int H, con
 namespace abx {
 template <int D>
 int launch_attention_tc5(cudaStream_t st, int B, int S, int L, int H, const float* q, const float* k, const float* v, int ld,
-                         const float* bias, const float* key_mask, const float* gate, float* out);
+                         const float* bias_tiles, const float* gate, float* out);
 template <int D> size_t attention_tc5_smem(int L);   // shared memory of the tcgen05 kernel (attention_tc5.cu) for key length L
 static bool tc5_fits(int L, int D) {
   switch (D) {
@@ -370,8 +370,15 @@ static bool tc5_fits(int L, int D) {
 }
 }  // namespace abx
 
-// impl: 0 = tcgen05 kernel (attention_tc5.cu; falls back to 2 when its operand tiles do not fit shared memory, i.e. D = 64),
-//       1 = SIMT kernel, 2 = mma.sync kernel
+namespace abx { int attention_tc5_profile(unsigned long long* out32); }
+// Diagnostics: the 32 per-role cycle counters CTA (0,0,0) of the last tcgen05 attention launch recorded (library built with
+// -DABX_ATTN_PROFILE=1; layout in attention_tc5.cu).
+extern "C" int abx_attention_profile(unsigned long long* out16) {
+  ABX_REQUIRE(out16 != nullptr, "abx_attention_profile: null output");
+  return abx::attention_tc5_profile(out16);
+}
+
+// impl: 0 or 2 = mma.sync kernel, 1 = SIMT kernel (the tcgen05 kernel takes the bias transposed: abx_pair_attention_tc5)
 extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, int D, const float* q, const float* k,
                                        const float* v, int ld, const float* bias, const float* key_mask, const float* gate,
                                        float* out) {
@@ -387,13 +394,6 @@ extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int
               "abx_pair_attention: q, k, v, out must be 16-byte aligned");
   ABX_REQUIRE((long long)B * S <= 65535, "abx_pair_attention: B*S exceeds 65535");
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 0 && tc5_fits(L, D) && (gate == nullptr || (uintptr_t)gate % 16 == 0)) {
-    switch (D) {
-      case 16: return launch_attention_tc5<16>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
-      case 32: return launch_attention_tc5<32>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
-      case 48: return launch_attention_tc5<48>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
-    }
-  }
   switch (D) {
     case 16: return launch_attention_mma<16>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
     case 32: return launch_attention_mma<32>(st, B, S, L, H, q, k, v, ld, bias, key_mask, gate, out);
@@ -403,3 +403,25 @@ extern "C" int abx_pair_attention_impl(void* stream, int impl, int B, int S, int
   set_error("abx_pair_attention: head dim %d not instantiated (16, 32, 48, 64)", D);
   return ABX_ERR_INVALID;
 }
+
+// tcgen05 kernel (attention_tc5.cu).  bias_tiles: the pair bias pre-tiled, pre-scaled and with the key mask folded in
+// (layout in include/abx_b200.h).
+extern "C" int abx_pair_attention_tc5(void* stream, int B, int S, int L, int H, int D, const float* q, const float* k, const float* v,
+                                      int ld, const float* bias_tiles, const float* gate, float* out) {
+  using namespace abx;
+  ABX_REQUIRE(B > 0 && S > 0 && L > 0 && H > 0 && q && k && v && bias_tiles && out, "abx_pair_attention_tc5: bad shape or null argument");
+  ABX_REQUIRE(ld % 4 == 0 && ld >= H * D, "abx_pair_attention_tc5: ld must be a multiple of 4 and >= H*D");
+  ABX_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                  (gate == nullptr || (uintptr_t)gate % 16 == 0),
+              "abx_pair_attention_tc5: q, k, v, gate, out must be 16-byte aligned");
+  ABX_REQUIRE((long long)B * S <= 65535, "abx_pair_attention_tc5: B*S exceeds 65535");
+  ABX_REQUIRE(tc5_fits(L, D), "abx_pair_attention_tc5: head dim %d not supported (D in {16,32,48})", D);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (D) {
+    case 16: return launch_attention_tc5<16>(st, B, S, L, H, q, k, v, ld, bias_tiles, gate, out);
+    case 32: return launch_attention_tc5<32>(st, B, S, L, H, q, k, v, ld, bias_tiles, gate, out);
+    default: return launch_attention_tc5<48>(st, B, S, L, H, q, k, v, ld, bias_tiles, gate, out);
+  }
+}
+
+extern "C" int abx_pair_attention_tc5_supported(int L, int D) { return abx::tc5_fits(L, D) ? 1 : 0; }

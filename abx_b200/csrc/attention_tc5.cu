@@ -20,7 +20,12 @@
 //   warp 12           MMA issuer.  Issue order  PV_0(kt), S_0(kt+1), PV_1(kt), S_1(kt+1), ...: while one slot's warpgroup runs
 //                     its softmax, the tensor core works on the other slot's products (ping-pong); `p_full` of a slot implies
 //                     that its S and O' columns have been read, so no further hand-shake is needed
-// The logits never leave the SM.
+// The logits never leave the SM.  The pair bias arrives PRE-TILED (abx_pair_attention_tc5 in include/abx_b200.h):
+//   bias_tiles[b][h][kt][it][j][i] = log2(e) * bias[b,h, 32 it + i, 64 kt + j]      (32 query rows x 64 keys per block),
+// with -FLT_MAX at masked keys (the reference's masked_fill(finfo.min): a softmax over masked keys only stays uniform) and -inf
+// at padding keys beyond L, so the kernel needs no mask logic and a warp's load of one key is a single 128-byte line at an
+// immediate offset (row-per-lane loads of the reference layout — rows of 1400 bytes at L = 350 — kept the LSU busy ~14k clk per
+// key tile).
 #include <float.h>
 
 #include "common.cuh"
@@ -30,7 +35,7 @@ namespace abx {
 namespace {
 
 constexpr int kTQ = 128, kTK = 64, kThreads = 512, kSoftThreads = 128, kLoadThreads = 128, kSlots = 2, kStagesKV = 2;
-constexpr int kRegsSoft = 192, kRegsLoad = 80, kRegsCtl = 40;   // 256 * 192 + 128 * (80 + 40) = 65536 - 1024 registers
+constexpr int kRegsSoft = 184, kRegsLoad = 80, kRegsCtl = 56;   // 256 * 184 + 128 * (80 + 56) = 65536 - 1024 registers
 constexpr uint32_t kSlotCols = 240;               // per query-tile slot: S [0,64) | P hi [64,128) | P lo [128,192) | O' [192, 192 + D)
 constexpr uint32_t kTmemCols = 512;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -133,16 +138,30 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 
 
+// Per-role wait / work cycle counters of CTA (0,0,0), compiled in with -DABX_ATTN_PROFILE=1 (read with abx_attention_profile):
+// [0] softmax WG0 wait O', [1] wait S, [2] total; [4] loader wait kv_empty, [5] total; [8] issuer wait kv_full, [9] wait P,
+// [10] issue (blocking tcgen05.mma / commit issue), [11] total; [12] key tiles.
+#ifndef ABX_ATTN_PROFILE
+#define ABX_ATTN_PROFILE 0
+#endif
+__device__ unsigned long long g_attn_prof[32];   // [16..21]: softmax WG0 phases: O' drain, S load, logits + max, exp + P store, store wait + arrive, bias issue
+#define ABX_ATTN_PWAIT(slot, bar, par)                                                  \
+  do {                                                                                  \
+    if (prof) { const long long t0__ = clock64(); mbar_wait(bar, par); pw[slot] += clock64() - t0__; } \
+    else mbar_wait(bar, par);                                                           \
+  } while (0)
+
 template <int D> struct Tc5Smem {
-  static constexpr uint32_t kLboQ = kTQ * 16 + 16, kLboK = kTK * 16 + 16, kLboV = D * 16 + 16;   // skewed column-block strides
+  // Column-block strides.  Q and K are NOT skewed: their 8-row x 16-byte core matrices must stay 128-byte aligned — a core
+  // matrix that straddles two 128-byte rows of shared memory costs the SS-mode MMA two wavefronts instead of one (measured:
+  // S = Q K^T at ~96 clk per MMA instead of 48).  V^T keeps a 16-byte skew (conflict-free transposing stores; its 12 core
+  // matrices per MMA stay below the MMA's own time even at two wavefronts each).
+  static constexpr uint32_t kLboQ = kTQ * 16, kLboK = kTK * 16, kLboV = D * 16 + 16;
   static constexpr uint32_t kQBytes = (D / 4) * kLboQ, kKBytes = (D / 4) * kLboK, kVBytes = (kTK / 4) * kLboV;
   static constexpr uint32_t kSlotBytes = 2 * kQBytes;                          // Q hi | Q lo
   static constexpr uint32_t kStageBytes = 2 * kKBytes + 2 * kVBytes;           // K hi | K lo | V^T hi | V^T lo
   static constexpr uint32_t q_base = 0, kv_base = kSlots * kSlotBytes, mask = kv_base + kStagesKV * kStageBytes;
-  __host__ __device__ static uint32_t total(int L) {                           // + key mask, tile flags, 10 mbarriers, TMEM slot
-    const uint32_t nkt = (uint32_t)((L + kTK - 1) / kTK);
-    return mask + nkt * kTK * 4 + ((nkt + 15) / 16) * 16 + 10 * 8 + 16;
-  }
+  __host__ __device__ static uint32_t total(int) { return mask + 10 * 8 + 16; }   // + 10 mbarriers, TMEM slot
 };
 
 }  // namespace
@@ -150,15 +169,13 @@ template <int D> struct Tc5Smem {
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
     int L, int H, int S, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
-    const float* __restrict__ bias, const float* __restrict__ key_mask, const float* __restrict__ gate, float scale,
-    float* __restrict__ out) {
+    const float* __restrict__ bias_tiles, const float* __restrict__ gate, float scale, float* __restrict__ out) {
   using SM = Tc5Smem<D>;
   constexpr int D4 = D / 4;
   extern __shared__ __align__(128) uint8_t sm[];
+  const long long tentry = clock64();
   const int nkt = (L + kTK - 1) / kTK, nqt = (L + kTQ - 1) / kTQ;
-  float* Ms = reinterpret_cast<float*>(sm + SM::mask);
-  uint8_t* tile_plain = sm + SM::mask + (size_t)nkt * kTK * 4;     // 1: every key of the tile is inside L and unmasked
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tile_plain + ((nkt + 15) / 16) * 16);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::mask);
   uint64_t* kv_full = bars;            // [2] loaders -> issuer
   uint64_t* kv_empty = bars + 2;       // [2] issuer (commit) -> loaders
   uint64_t* s_full = bars + 4;         // [2 slots] issuer (commit) -> softmax warpgroup
@@ -184,32 +201,40 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int j = threadIdx.x; j < nkt * kTK; j += kThreads) Ms[j] = (j < L) ? (key_mask ? __ldg(key_mask + (size_t)b * L + j) : 1.f) : 0.f;
-  // Q tiles of the slots, pre-multiplied by log2(e) / sqrt(D): hi / lo, K-major core matrices
-  for (int idx = threadIdx.x; idx < nslots * kTQ * D4; idx += kThreads) {
-    const int i = idx / D4, c4 = idx % D4, slot = i / kTQ, il = i % kTQ;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + i < L) x = *reinterpret_cast<const float4*>(q + (row0 + q0 + i) * (size_t)ld + h * D + 4 * c4);
-    x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
-    float4 hi, lo;
-    hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-    hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-    lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
-    const uint32_t off = SM::q_base + slot * SM::kSlotBytes + c4 * SM::kLboQ + il * 16;
-    *reinterpret_cast<float4*>(sm + off) = hi;
-    *reinterpret_cast<float4*>(sm + off + SM::kQBytes) = lo;
-  }
-  __syncthreads();
-  if (threadIdx.x < nkt) {
-    bool plain = (threadIdx.x + 1) * kTK <= L;
-    for (int u = 0; u < kTK && plain; ++u) plain = Ms[threadIdx.x * kTK + u] != 0.f;
-    tile_plain[threadIdx.x] = plain ? 1 : 0;
+  // Q tiles of the slots, pre-multiplied by log2(e) / sqrt(D): hi / lo, K-major core matrices.  Thread <-> (row, half of the
+  // row's 16-byte blocks) with the row fastest: a warp's stores of one block are 32 consecutive rows = 512 contiguous bytes.
+  {
+    constexpr int kRun = D4 / 2;
+    const int rows = nslots * kTQ;
+    for (int item = threadIdx.x; item < 2 * rows; item += kThreads) {
+      const int i = item % rows, run = item / rows, slot = i / kTQ, il = i % kTQ;
+      const bool ok = q0 + i < L;
+      const float* src = q + (row0 + q0 + (ok ? i : 0)) * (size_t)ld + h * D + 4 * run * kRun;
+      float4 x[kRun];
+#pragma unroll
+      for (int u = 0; u < kRun; ++u) x[u] = ok ? *reinterpret_cast<const float4*>(src + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kRun; ++u) {
+        float4 v = x[u], hi, lo;
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+        const uint32_t off = SM::q_base + slot * SM::kSlotBytes + (run * kRun + u) * SM::kLboQ + il * 16;
+        *reinterpret_cast<float4*>(sm + off) = hi;
+        *reinterpret_cast<float4*>(sm + off + SM::kQBytes) = lo;
+      }
+    }
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool prof = ABX_ATTN_PROFILE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  unsigned long long pw[3] = {0, 0, 0};
+  const long long tstart = clock64();
+  if (prof && threadIdx.x == 0) g_attn_prof[13] = tstart - tentry;     // prologue: barriers, TMEM allocation, mask, Q staging
 
   if (warp < 8) {
     // ================= softmax / accumulator warpgroups: thread = query row = tensor-memory lane =================
@@ -218,33 +243,29 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
     if (slot < nslots) {
       const int i = q0 + slot * kTQ + (threadIdx.x & (kSoftThreads - 1));   // query row of this thread
       const bool row_ok = i < L;
-      const float* brow = bias + (((size_t)b * H + h) * L + (row_ok ? i : L - 1)) * L;
+      const int nit = (L + 31) / 32;                   // 32-row blocks of the tiled bias; rows beyond them read the last block
+      const size_t tile_stride = (size_t)nit * (kTK * 32);
+      const float* bt = bias_tiles + ((size_t)(b * H + h) * nkt * nit + min(i >> 5, nit - 1)) * (kTK * 32) + lane;
       const uint32_t lane_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + slot * kSlotCols;
-      const bool vec_bias = (L % 4) == 0;              // 16-byte bias loads need 16-byte aligned rows
-      auto load_bias = [&](int j, float (&dst)[16]) {  // pair bias of this row for keys j .. j + 15 (0 beyond L)
-        if (vec_bias && j + 16 <= L) {
+      auto load_bias = [&](const float* tile, int c0, float (&dst)[16]) {   // keys c0 .. c0 + 15 of a key tile, this lane's row
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(brow + j) + u);
-            dst[4 * u] = t4.x; dst[4 * u + 1] = t4.y; dst[4 * u + 2] = t4.z; dst[4 * u + 3] = t4.w;
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 16; ++u) dst[u] = (j + u < L) ? __ldg(brow + j + u) : 0.f;
-        }
+        for (int u = 0; u < 16; ++u) dst[u] = __ldg(tile + (c0 + u) * 32);
       };
       float acc[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) acc[d] = 0.f;
       float m = -FLT_MAX, l = 0.f;
       float bv0[16], bv1[16], bv2[16], bv3[16];
-      load_bias(0, bv0);
-      load_bias(16, bv1);
+      unsigned long long ph[6] = {0, 0, 0, 0, 0, 0};
+      long long tp = 0;
+#define ABX_PH(k) do { if (prof) { const long long n__ = clock64(); ph[k] += n__ - tp; tp = n__; } } while (0)
+      load_bias(bt, 0, bv0);
+      load_bias(bt, 16, bv1);
       for (int kt = 0; kt < nkt; ++kt) {
-        const int j0 = kt * kTK;
         const uint32_t par = kt & 1;
         if (kt > 0) {                                  // O' of the previous tile (relative to the same reference point as acc)
-          mbar_wait(o_full + slot, par ^ 1);
+          ABX_ATTN_PWAIT(0, o_full + slot, par ^ 1);
+          if (prof) tp = clock64();
           tc_fence_after();
           float t[D];
 #pragma unroll
@@ -252,37 +273,40 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
           tmem_ld_wait();
 #pragma unroll
           for (int d = 0; d < D; ++d) acc[d] += t[d];
+          ABX_PH(0);
         }
-        load_bias(j0 + 32, bv2);
-        load_bias(j0 + 48, bv3);
-        mbar_wait(s_full + slot, par);                 // S = Q K^T of this tile
+        if (prof) tp = clock64();
+        load_bias(bt, 32, bv2);
+        load_bias(bt, 48, bv3);
+        ABX_PH(5);
+        ABX_ATTN_PWAIT(1, s_full + slot, par);         // S = Q K^T of this tile
         tc_fence_after();
+        if (prof) tp = clock64();
+        // S is read and biased in two halves of 32 keys: never more than acc (D) + 64 logits + 32 bias values live — with all
+        // 64 bias values and 64 logits in flight at once the loop spilled, and loaded bias values went straight to local memory
         float sv[kTK];
-#pragma unroll
-        for (int c0 = 0; c0 < kTK; c0 += 16) tmem_ld16_nowait(lane_base + c0, sv + c0);
-        tmem_ld_wait();
-        const bool plain = tile_plain[kt] != 0;
         float cm = -FLT_MAX;
-        auto chunk = [&](int c0, const float (&bv)[16]) {   // base-2 logits of keys j0 + c0 .. + 15
+        auto chunk = [&](int c0, const float (&bv)[16]) {   // base-2 logits of keys j0 + c0 .. + 15 (mask and padding ride in the bias)
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            float a = fmaf(bv[u], kLog2e, sv[c0 + u]);
-            if (!plain) {                                   // masked_fill(finfo.min); padding keys contribute exactly 0
-              const int j = j0 + c0 + u;
-              a = (j < L) ? ((Ms[j] != 0.f) ? a : -FLT_MAX) : -INFINITY;
-            }
+            const float a = sv[c0 + u] + bv[u];
             sv[c0 + u] = a;
             cm = fmaxf(cm, a);
           }
         };
+        tmem_ld16_nowait(lane_base, sv);
+        tmem_ld16_nowait(lane_base + 16, sv + 16);
+        tmem_ld_wait();
+        ABX_PH(1);
         chunk(0, bv0);
         chunk(16, bv1);
-        if (kt + 1 < nkt) {                            // first half of the next tile's bias: in flight during the rest of this tile
-          load_bias(j0 + kTK, bv0);
-          load_bias(j0 + kTK + 16, bv1);
-        }
+        tmem_ld16_nowait(lane_base + 32, sv + 32);
+        tmem_ld16_nowait(lane_base + 48, sv + 48);
+        tmem_ld_wait();
         chunk(32, bv2);
         chunk(48, bv3);
+        bt += tile_stride;
+        ABX_PH(2);
         const float mn = fmaxf(m, cm);
         const float alpha = ex2_ftz(m - mn);
         m = mn;
@@ -303,12 +327,20 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
         l = fmaf(l, alpha, psum);
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] *= alpha;
+        if (kt + 1 < nkt) {                            // first half of the next tile's bias: lands during the waits for O' and S
+          load_bias(bt, 0, bv0);
+          load_bias(bt, 16, bv1);
+        }
+        ABX_PH(3);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(p_full + slot);                    // P written; S and O' of this slot have been read
+        ABX_PH(4);
       }
+      if (prof && threadIdx.x == 0)
+        for (int k2 = 0; k2 < 6; ++k2) g_attn_prof[16 + k2] = ph[k2];
       {
-        mbar_wait(o_full + slot, (nkt - 1) & 1);
+        ABX_ATTN_PWAIT(0, o_full + slot, (nkt - 1) & 1);
         tc_fence_after();
         float t[D];
 #pragma unroll
@@ -317,6 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] += t[d];
       }
+      if (prof && threadIdx.x == 0) { g_attn_prof[0] = pw[0]; g_attn_prof[1] = pw[1]; g_attn_prof[2] = clock64() - tstart; g_attn_prof[12] = nkt; }
+      const long long tstore = clock64();
       if (row_ok) {
         const float inv = 1.f / l;
         const size_t HD = (size_t)H * D;
@@ -333,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
           *reinterpret_cast<float4*>(orow + d) = o;
         }
       }
+      if (prof && threadIdx.x == 0) g_attn_prof[14] = clock64() - tstore;   // output (gate loads + stores issued)
     }
   } else if (warp < 12) {
     // ================= loader warps: K / V tile -> hi / lo operand tiles, two stages =================
@@ -341,19 +376,21 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
     constexpr int kPer = kTK * D4 / kLoadThreads;    // float4 per thread and matrix (D = 48: 6)
     static_assert(kTK * D4 % kLoadThreads == 0, "tile must divide over the loader threads");
     float4 kreg[kPer], vreg[kPer];
-    // K: thread <-> (key, 16-byte block) with the block index fastest: coalesced global reads, conflict-free 16-byte stores.
-    // V: thread <-> key (fastest) x a run of kPer consecutive 16-byte blocks of that key's row: the transposing scalar stores of
-    // a warp then go to 32 consecutive keys of one channel row = 32 distinct banks (each thread still reads whole 32-byte sectors).
+    // K and V: thread <-> key (fastest) x a run of kPer consecutive 16-byte blocks of that key's row (whole 32-byte sectors per
+    // thread).  K stores: a warp writes one block of 32 consecutive keys = 512 contiguous bytes; V stores (transposing, scalar):
+    // 32 consecutive keys of one channel row = 32 distinct banks.
     const int vkey = t % kTK, vc0 = (t / kTK) * kPer;
-    static_assert(kLoadThreads / kTK * kPer == D4, "V mapping must cover the row");
+    static_assert(kLoadThreads / kTK * kPer == D4, "mapping must cover the row");
     auto fetch = [&](int kt) {                       // global -> registers (the next tile's loads are in flight during the math)
+      const int jv = kt * kTK + vkey;
+      const size_t ro = (row0 + (jv < L ? jv : 0)) * (size_t)ld + h * D + 4 * vc0;
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
-        const int idx = t + u * kLoadThreads, j = kt * kTK + idx / D4, c4 = idx % D4;
         kreg[u] = vreg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < L) kreg[u] = *reinterpret_cast<const float4*>(k + (row0 + j) * (size_t)ld + h * D + 4 * c4);
-        const int jv = kt * kTK + vkey;
-        if (jv < L) vreg[u] = *reinterpret_cast<const float4*>(v + (row0 + jv) * (size_t)ld + h * D + 4 * (vc0 + u));
+        if (jv < L) {
+          kreg[u] = *reinterpret_cast<const float4*>(k + ro + 4 * u);
+          vreg[u] = *reinterpret_cast<const float4*>(v + ro + 4 * u);
+        }
       }
     };
     auto split4 = [](const float4& x, float4& hi, float4& lo) {
@@ -365,10 +402,9 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
       uint8_t* k_hi = st, *k_lo = st + SM::kKBytes, *v_hi = st + 2 * SM::kKBytes, *v_lo = v_hi + SM::kVBytes;
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
-        const int idx = t + u * kLoadThreads, jj = idx / D4, c4 = idx % D4;
         float4 hi, lo;
-        split4(kreg[u], hi, lo);                     // K tile: rows = keys, 16-byte column block c4
-        const uint32_t ko = c4 * SM::kLboK + jj * 16;
+        split4(kreg[u], hi, lo);                     // K tile: rows = keys, 16-byte column block vc0 + u
+        const uint32_t ko = (vc0 + u) * SM::kLboK + vkey * 16;
         *reinterpret_cast<float4*>(k_hi + ko) = hi;
         *reinterpret_cast<float4*>(k_lo + ko) = lo;
         split4(vreg[u], hi, lo);                     // V^T tile: rows = channels 4 c .. 4 c + 3, column block vkey / 4, element vkey % 4
@@ -382,12 +418,13 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
     fetch(0);
     for (int kt = 0; kt < nkt; ++kt) {
       const int st = kt & 1;
-      if (kt >= kStagesKV) mbar_wait(kv_empty + st, ((kt >> 1) - 1) & 1);   // the products of tile kt - 2 have read the stage
+      if (kt >= kStagesKV) ABX_ATTN_PWAIT(0, kv_empty + st, ((kt >> 1) - 1) & 1);   // the products of tile kt - 2 have read the stage
       stage(sm + SM::kv_base + st * SM::kStageBytes);
       fence_proxy_async();
       mbar_arrive(kv_full + st);
       if (kt + 1 < nkt) fetch(kt + 1);
     }
+    if (prof && t == 0) { g_attn_prof[4] = pw[0]; g_attn_prof[5] = clock64() - tstart; }
   } else {
     // ================= MMA issuer (warp 12); warps 13-15 only hold the tensor-memory allocation =================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
@@ -426,25 +463,30 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
         umma_commit(o_full + slot);
       };
       if (elect_one()) {
-        mbar_wait(kv_full + 0, 0);
+        ABX_ATTN_PWAIT(0, kv_full + 0, 0);
         tc_fence_after();
         for (int slot = 0; slot < nslots; ++slot) issue_s(slot, 0);
         for (int kt = 0; kt < nkt; ++kt) {
           const int st = kt & 1;
           for (int slot = 0; slot < nslots; ++slot) {
-            mbar_wait(p_full + slot, kt & 1);
+            ABX_ATTN_PWAIT(1, p_full + slot, kt & 1);
+            const long long ti = prof ? clock64() : 0;
             tc_fence_after();
             issue_pv(slot, st);
             if (slot == nslots - 1) umma_commit(kv_empty + st);     // every product reading stage st has been issued
             if (kt + 1 < nkt) {
               if (slot == 0) {
+                const long long tw = prof ? clock64() : 0;
                 mbar_wait(kv_full + (st ^ 1), ((kt + 1) >> 1) & 1);
+                if (prof) { const long long d = clock64() - tw; pw[0] += d; pw[2] -= d; }
                 tc_fence_after();
               }
               issue_s(slot, st ^ 1);
             }
+            if (prof) pw[2] += clock64() - ti;
           }
         }
+        if (prof) { g_attn_prof[8] = pw[0]; g_attn_prof[9] = pw[1]; g_attn_prof[10] = pw[2]; g_attn_prof[11] = clock64() - tstart; }
       }
       __syncwarp();
     }
@@ -452,6 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
 
   tc_fence_before();
   __syncthreads();
+  if (prof && threadIdx.x == 0) g_attn_prof[15] = clock64() - tentry;       // whole CTA up to the final barrier
   if (warp == 13) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -460,15 +503,21 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
 
 template <int D>
 int launch_attention_tc5(cudaStream_t st, int B, int S, int L, int H, const float* q, const float* k, const float* v, int ld,
-                         const float* bias, const float* key_mask, const float* gate, float* out) {
+                         const float* bias_tiles, const float* gate, float* out) {
   const size_t smem = Tc5Smem<D>::total(L);
   ABX_REQUIRE(smem <= 227 * 1024, "abx_pair_attention: L=%d with head dim %d needs %zu bytes of shared memory per CTA", L, D, smem);
   ABX_CUDA(cudaFuncSetAttribute(pair_attention_tc5_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nqt = (L + kTQ - 1) / kTQ;
   pair_attention_tc5_kernel<D><<<dim3(H, B * S, (nqt + kSlots - 1) / kSlots), kThreads, smem, st>>>(
-      L, H, S, q, k, v, ld, bias, key_mask, gate, kLog2e / sqrtf((float)D), out);
+      L, H, S, q, k, v, ld, bias_tiles, gate, kLog2e / sqrtf((float)D), out);
   count_launch();
   return check_launch("pair_attention_tc5_kernel");
+}
+
+int attention_tc5_profile(unsigned long long* out16) {  // 32 counters
+  ABX_CUDA(cudaDeviceSynchronize());
+  ABX_CUDA(cudaMemcpyFromSymbol(out16, g_attn_prof, sizeof(g_attn_prof)));
+  return ABX_OK;
 }
 
 // shared memory the kernel needs for key length L (the dispatcher falls back to the mma.sync kernel beyond 227 KB: D = 64)
@@ -478,10 +527,10 @@ template size_t attention_tc5_smem<32>(int);
 template size_t attention_tc5_smem<48>(int);
 
 template int launch_attention_tc5<16>(cudaStream_t, int, int, int, int, const float*, const float*, const float*, int, const float*,
-                                      const float*, const float*, float*);
+                                      const float*, float*);
 template int launch_attention_tc5<32>(cudaStream_t, int, int, int, int, const float*, const float*, const float*, int, const float*,
-                                      const float*, const float*, float*);
+                                      const float*, float*);
 template int launch_attention_tc5<48>(cudaStream_t, int, int, int, int, const float*, const float*, const float*, int, const float*,
-                                      const float*, const float*, float*);
+                                      const float*, float*);
 
 }  // namespace abx

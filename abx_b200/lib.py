@@ -51,8 +51,11 @@ SIGNATURES = {
     'abx_layernorm': (_i, [_vp, C.c_longlong, _i, _vp, _vp, _vp, C.c_float, _i, _vp]),
     'abx_pair_attention': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     'abx_pair_attention_impl': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    'abx_pair_attention_tc5': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    'abx_pair_attention_tc5_supported': (_i, [_i, _i]),
     'abx_set_gemm_backend': (_i, [_i]),
     'abx_gemm_profile': (_i, [_vp]),
+    'abx_attention_profile': (_i, [_vp]),
     'abx_ipa_frame_update': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'abx_ipa_workspace_bytes': (_sz, [_i, _i]),
     'abx_ipa_pair_bias_floats': (_sz, [_i, _i]),

@@ -60,11 +60,24 @@ def layer_norm(x, weight, bias, eps=1e-5, transpose_n=0):
     return y
 
 
-def pair_attention(qkv, bias, key_mask, num_head, impl='mma', gated=False):
+def _bias_tiles(bias, key_mask):
+    """Pair bias [B,H,L,L] (+ key mask [B,L]) in the layout of abx_pair_attention_tc5 (include/abx_b200.h): blocks of 32 query rows
+    x 64 keys, key-major inside a block, scaled by log2(e); masked keys -> finfo.min, padding keys -> -inf."""
+    B, H, L, _ = bias.shape
+    Lq, Lk = (L + 31) // 32 * 32, (L + 63) // 64 * 64
+    t = torch.zeros(B, H, Lq, Lk, device=bias.device, dtype=torch.float32)
+    t[:, :, :, L:] = float('-inf')
+    t[:, :, :L, :L] = bias * 1.4426950408889634
+    if key_mask is not None:
+        t[:, :, :, :L].masked_fill_(~key_mask.to(torch.bool)[:, None, None, :], torch.finfo(torch.float32).min)
+    return t.view(B, H, Lq // 32, 32, Lk // 64, 64).permute(0, 1, 4, 2, 5, 3).contiguous()
+
+
+def pair_attention(qkv, bias, key_mask, num_head, impl='tc5', gated=False):
     """Fused attention core for TriangleAttention.  qkv [B,S,L,3*H*D] (q | k | v slices of one projection;
     with `gated=True` [B,S,L,4*H*D] = q | k | v | gate pre-activation), bias [B,H,L,L], key_mask [B,L]
     (bool/float, None = keep all)  ->  [B,S,L,H*D] (times sigmoid(gate) when gated).
-    impl: 'mma' (mma.sync 3xTF32, default), 'tc5' (tcgen05 3xTF32) or 'simt'."""
+    impl: 'tc5' (tcgen05 3xTF32, default; head dim 64 falls back to 'mma'), 'mma' (mma.sync 3xTF32) or 'simt'."""
     L_ = lib.load()
     B, S, L, Cw = qkv.shape
     HD = Cw // (4 if gated else 3)
@@ -75,9 +88,14 @@ def pair_attention(qkv, bias, key_mask, num_head, impl='mma', gated=False):
     out = torch.empty(B, S, L, HD, device=qkv.device, dtype=torch.float32)
     base, esz = qkv.data_ptr(), 4
     with lib.device_guard(qkv):
-        lib.check(L_.abx_pair_attention_impl(lib.stream(), {'tc5': 0, 'simt': 1, 'mma': 2}[impl], B, S, L, num_head, D, base,
-                                             base + HD * esz, base + 2 * HD * esz, Cw,
-                                             lib.ptr(bias), lib.ptr(km), (base + 3 * HD * esz) if gated else None, lib.ptr(out)))
+        if impl == 'tc5' and L_.abx_pair_attention_tc5_supported(L, D):
+            lib.check(L_.abx_pair_attention_tc5(lib.stream(), B, S, L, num_head, D, base, base + HD * esz, base + 2 * HD * esz, Cw,
+                                                lib.ptr(_bias_tiles(bias, key_mask)), (base + 3 * HD * esz) if gated else None,
+                                                lib.ptr(out)))
+        else:
+            lib.check(L_.abx_pair_attention_impl(lib.stream(), {'tc5': 2, 'simt': 1, 'mma': 2}[impl], B, S, L, num_head, D, base,
+                                                 base + HD * esz, base + 2 * HD * esz, Cw,
+                                                 lib.ptr(bias), lib.ptr(km), (base + 3 * HD * esz) if gated else None, lib.ptr(out)))
     return out
 
 

@@ -176,13 +176,24 @@ int abx_outer_product(void* stream, int B, int N, int C, const float* left, cons
  *   D in {16,32,48,64}; 2*L*D*4 bytes of K/V must fit in shared memory (L <= ~520 at D = 48). */
 int abx_pair_attention(void* stream, int B, int S, int L, int H, int D, const float* q, const float* k,
                        const float* v, int ld, const float* bias, const float* key_mask, float* out);
-/* Same operation with a choice of implementation: impl 0 = tensor-core kernel (mma.sync m16n8k8 TF32 with the
+/* Same operation with a choice of implementation: impl 0 / 2 = tensor-core kernel (mma.sync m16n8k8 TF32 with the
  * 3xTF32 operand split, FlashAttention-2 dataflow in registers), impl 1 = the SIMT kernel above.
- * gate (impl 0 only, may be NULL): pre-activation of the output gate laid out like q (row stride ld);
+ * gate (impl 0 / 2 only, may be NULL): pre-activation of the output gate laid out like q (row stride ld);
  * out = sigmoid(gate) * attention  (seqformer.py:296-299) — with q|k|v|gate produced by one GEMM. */
 int abx_pair_attention_impl(void* stream, int impl, int B, int S, int L, int H, int D, const float* q, const float* k,
                             const float* v, int ld, const float* bias, const float* key_mask, const float* gate,
                             float* out);
+/* Same operation on the 5th-generation tensor cores (tcgen05.mma 3xTF32, S / P / O' in tensor memory, two 128-row query
+ * tiles per CTA).  The pair bias and the key mask arrive pre-tiled in ONE tensor
+ *   bias_tiles[b][h][kt][it][j][i], kt < ceil(L/64), it < ceil(L/32), j < 64, i < 32
+ *     = log2(e) * bias[b,h, 32 it + i, 64 kt + j]   for keys inside L with key_mask != 0
+ *     = -FLT_MAX                                    for keys with key_mask == 0 (the reference's masked_fill(finfo.min))
+ *     = -inf                                        for padding keys 64 kt + j >= L  (rows beyond L: any finite value)
+ * (abx_b200.ops.pair_attention builds it with three torch ops).  D in {16,32,48}; q, k, v, gate, out 16-byte aligned.
+ * abx_pair_attention_tc5_supported(L, D) tells whether the operand tiles fit (1) or not (0). */
+int abx_pair_attention_tc5(void* stream, int B, int S, int L, int H, int D, const float* q, const float* k,
+                           const float* v, int ld, const float* bias_tiles, const float* gate, float* out);
+int abx_pair_attention_tc5_supported(int L, int D);
 
 /* Which GEMM the IPA pipeline uses for its node layers: 0 auto (tcgen05 when operands qualify),
  * 1 SIMT (abx_linear_f32), 2 tcgen05 only.  Process-wide; meant for A/B measurements and tests. */
@@ -191,6 +202,9 @@ int abx_set_gemm_backend(int backend);
 /* Diagnostics of abx_gemm_tf32x3 (no reference counterpart): with ABX_GEMM_PROF=1 in the environment CTA 0 of every
  * launch records per-role wait / work cycle counters; this copies the 32 counters of the last launch (host buffer). */
 int abx_gemm_profile(unsigned long long* out32);
+
+/* Same for the tcgen05 triangle-attention kernel (library built with -DABX_ATTN_PROFILE=1): 32 counters of CTA (0,0,0). */
+int abx_attention_profile(unsigned long long* out32);
 
 /* ---- Invariant Point Attention ---------------------------------------------------------------- */
 /* Weights of abx.model.folding.InvariantPointAttention (folding.py:23-45), reference state_dict

@@ -25,3 +25,14 @@ for impl in ('tc5', 'mma'):
         ref = torch.einsum('bshqk,bshkd->bsqhd', w, v).reshape(1, 8, L, H * D)
     err = float((out[:1, :8].double() - ref).abs().max())
     print(json.dumps(dict(impl=impl, ms=ms, tflops=flops / ms / 1e9, maxerr=err)))
+if os.environ.get('ABX_ATTN_PROF') == '1':
+    import ctypes
+    from abx_b200 import lib
+    out = ops.pair_attention(qkv, bias, mask, H, impl='tc5')
+    buf = (ctypes.c_ulonglong * 32)()
+    lib.check(lib.load().abx_attention_profile(buf))
+    names = {0: 'soft0_wait_o', 1: 'soft0_wait_s', 2: 'soft0_total', 4: 'load_wait_empty', 5: 'load_total', 8: 'mma_wait_kv', 9: 'mma_wait_p',
+             10: 'mma_issue', 11: 'mma_total', 12: 'key_tiles', 13: 'prologue', 14: 'store', 15: 'cta_total',
+             16: 'ph_drain_o', 17: 'ph_load_s', 18: 'ph_logits_max', 19: 'ph_exp_stP', 20: 'ph_stwait_arrive', 21: 'ph_bias_issue'}
+    nk = max(int(buf[12]), 1)
+    print(json.dumps({'cycles_per_key_tile': {v: round(int(buf[i]) / nk, 1) for i, v in names.items() if i != 12}, 'key_tiles': nk}))
