@@ -361,8 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
           float4 o = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
           if (grow) {                                  // out = sigmoid(gate) * attention  (seqformer.py:296-299)
             const float4 g4 = *reinterpret_cast<const float4*>(grow + d);
-            o.x *= 1.f / (1.f + expf(-g4.x)); o.y *= 1.f / (1.f + expf(-g4.y));
-            o.z *= 1.f / (1.f + expf(-g4.z)); o.w *= 1.f / (1.f + expf(-g4.w));
+            o.x *= sigmoid_fast(g4.x); o.y *= sigmoid_fast(g4.y);
+            o.z *= sigmoid_fast(g4.z); o.w *= sigmoid_fast(g4.w);
           }
           *reinterpret_cast<float4*>(orow + d) = o;
         }

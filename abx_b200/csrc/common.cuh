@@ -33,6 +33,15 @@ int check_launch(const char* what);   // cudaGetLastError after a launch -> ABX_
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Logistic function without slow paths: 1 / (1 + 2^(-x log2 e)) on the bare MUFU.EX2 / MUFU.RCP (4 instructions; expf + an IEEE
+// division is ~25 with two special-case branches, which made the gated GEMM epilogues compute-bound).  |error| < 4e-7.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in
 // the stream is still draining; it must execute griddep_wait() before it touches anything the predecessor

@@ -186,9 +186,9 @@ template <int ACT>
 __device__ __forceinline__ float epilogue_op(float a, float bias, float gate, float scale, float res) {
   a += bias;
   if (ACT == 1) a = fmaxf(a, 0.f);
-  else if (ACT == 2) a = a * (1.f / (1.f + expf(-gate)));
-  else if (ACT == 3) a = 1.f / (1.f + expf(-a));
-  else if (ACT == 4) a = gate * (1.f / (1.f + expf(-a)));
+  else if (ACT == 2) a = a * sigmoid_fast(gate);
+  else if (ACT == 3) a = sigmoid_fast(a);
+  else if (ACT == 4) a = gate * sigmoid_fast(a);
   return a * scale + res;
 }
 
@@ -330,7 +330,7 @@ __device__ __forceinline__ void store_row_glu(const float (&acc)[BN], const Epil
 #pragma unroll
     for (int c = 0; c < HB; ++c) {
       const float pb = ep.bias ? __ldg(ep.bias + n0 + c) : 0.f, gb = ep.bias ? __ldg(ep.bias + n0 + HB + c) : 0.f;
-      yc[c * cstride] = (acc[c] + pb) * (1.f / (1.f + expf(-(acc[HB + c] + gb)))) * sc;
+      yc[c * cstride] = (acc[c] + pb) * sigmoid_fast(acc[HB + c] + gb) * sc;
     }
     return;
   }
@@ -341,7 +341,7 @@ __device__ __forceinline__ void store_row_glu(const float (&acc)[BN], const Epil
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float pb = ep.bias ? __ldg(ep.bias + n0 + c + u) : 0.f, gb = ep.bias ? __ldg(ep.bias + n0 + HB + c + u) : 0.f;
-      o[u] = (acc[c + u] + pb) * (1.f / (1.f + expf(-(acc[HB + c + u] + gb)))) * sc;
+      o[u] = (acc[c + u] + pb) * sigmoid_fast(acc[HB + c + u] + gb) * sc;
     }
     *reinterpret_cast<float4*>(yr + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
