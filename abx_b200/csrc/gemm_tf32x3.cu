@@ -351,8 +351,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
-                   int Nout, int K, Epilogue ep, float* __restrict__ y, int ldy, int trust_trunc, int kb_per_drain,
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_blo, int has_blo, int M, int Nout, int K, Epilogue ep, float* __restrict__ y, int ldy, int trust_trunc, int kb_per_drain,
                    int splits, long long split_stride, Batched bt) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
@@ -432,9 +432,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const uint32_t ph = (it / kStages) & 1;
           ABX_GEMM_PWAIT(0, empty + s, ph ^ 1);
           if (trust_trunc & 16) { mbar_arrive(full + s); continue; }      // timing probe: no TMA at all
-          mbar_expect_tx(full + s, kTileABytes + Cfg::kTileBBytes);
+          mbar_expect_tx(full + s, kTileABytes + Cfg::kTileBBytes * (has_blo ? 2u : 1u));
           tma_load_2d(stage_a(s), &map_a, full + s, (kb0 + kb) * kBK, m0);
           tma_load_2d(stage_b(s), &map_b, full + s, (kb0 + kb) * kBK, n0);
+          if (has_blo) tma_load_2d(stage_blo(s), &map_blo, full + s, (kb0 + kb) * kBK, n0);   // precomputed lo part of a static weight
         }
       }
       if (prof) { g_gemm_prof[0] = pw[0]; g_gemm_prof[1] = clock64() - tstart; g_gemm_prof[2] = it; }
@@ -575,8 +576,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             tmem_st16(ta + kBK + 16 * half, lo);
           }
         }
-        // W: lo tile next to the raw tile (element-wise, layout preserved)
-        {
+        // W: lo tile next to the raw tile (element-wise, layout preserved) — unless the caller supplied it (static weights)
+        if (!has_blo) {
           const float4* b = reinterpret_cast<const float4*>(stage_b(s));
           float4* blo = reinterpret_cast<float4*>(stage_blo(s));
 #pragma unroll 8
@@ -782,12 +783,13 @@ GemmTimingTable& gemm_timing_table() {
 template <int BN>
 int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw, const Epilogue& ep,
               float* y, int ldy, int splits = 1, long long split_stride = 0, Batched bt = Batched{0, 0, 1, 0},
-              int map_rows_a = 0, int map_rows_b = 0) {
+              int map_rows_a = 0, int map_rows_b = 0, const float* w_lo = nullptr) {
   using Cfg = GemmCfg<BN>;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mblo;
   int rc;
   if ((rc = make_map(&ma, x, map_rows_a ? map_rows_a : M, K, ldx, kBM))) return rc;
   if ((rc = make_map(&mb, w, map_rows_b ? map_rows_b : Nout, K, ldw, BN))) return rc;
+  if ((rc = make_map(&mblo, w_lo ? w_lo : w, map_rows_b ? map_rows_b : Nout, K, ldw, BN))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     ABX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
@@ -801,8 +803,8 @@ int launch_bn(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, c
     cudaEventCreate(&e1);
     cudaEventRecord(e0, s);
   }
-  const cudaError_t le = launch_kernel(gemm_tf32x3_kernel<BN>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, s, ma, mb, M, Nout, K, ep,
-                                       y, ldy, trust_trunc(), kb_per_drain(), splits, split_stride, bt);
+  const cudaError_t le = launch_kernel(gemm_tf32x3_kernel<BN>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, s, ma, mb, mblo,
+                                       w_lo ? 1 : 0, M, Nout, K, ep, y, ldy, trust_trunc(), kb_per_drain(), splits, split_stride, bt);
   if (e0) {
     cudaEventRecord(e1, s);
     cudaEventSynchronize(e1);
@@ -836,7 +838,7 @@ bool gemm_tf32x3_supported(int M, int Nout, int K, const float* x, int ldx, cons
 // act: see Epilogue.  tile_n: 0 = choose, else 32/64/128.
 int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                        const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
-                       int transpose_n, float* y, int ldy, int tile_n, int cm_n = 0, int cm_np = 0) {
+                       int transpose_n, float* y, int ldy, int tile_n, int cm_n = 0, int cm_np = 0, const float* w_lo = nullptr) {
   Epilogue ep{bias, residual, gate, row_scale, act, transpose_n, cm_n, cm_np};
   if (tile_n == 0) {
     // enough CTAs to cover the 148 SMs beats wide tiles for the small-M node GEMMs
@@ -847,9 +849,9 @@ int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, i
     else tile_n = 128;
   }
   switch (tile_n) {
-    case 32: return launch_bn<32>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy);
-    case 64: return launch_bn<64>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy);
-    case 128: return launch_bn<128>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy);
+    case 32: return launch_bn<32>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy, 1, 0, Batched{0, 0, 1, 0}, 0, 0, w_lo);
+    case 64: return launch_bn<64>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy, 1, 0, Batched{0, 0, 1, 0}, 0, 0, w_lo);
+    case 128: return launch_bn<128>(s, M, Nout, K, x, ldx, w, ldw, ep, y, ldy, 1, 0, Batched{0, 0, 1, 0}, 0, 0, w_lo);
   }
   set_error("abx_gemm_tf32x3: tile_n must be 0, 32, 64 or 128 (got %d)", tile_n);
   return ABX_ERR_INVALID;
@@ -904,9 +906,9 @@ extern "C" int abx_gemm_tf32x3_batched_nt(void* stream, int batches, int n, int 
   return abx::launch_gemm_tf32x3_batched_nt((cudaStream_t)stream, batches, n, kpad, inner, outer_rows, total_rows, a, b, out, ldo);
 }
 
-extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
-                               const float* bias, const float* residual, const float* gate, const float* row_scale,
-                               int act, int transpose_n, float* y, int ldy, int tile_n) {
+extern "C" int abx_gemm_tf32x3_wlo(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, const float* w_lo,
+                                   int ldw, const float* bias, const float* residual, const float* gate, const float* row_scale,
+                                   int act, int transpose_n, float* y, int ldy, int tile_n) {
   ABX_REQUIRE(M > 0 && Nout > 0 && K > 0 && x && w && y, "abx_gemm_tf32x3: bad shape or null argument");
   ABX_REQUIRE(abx::gemm_tf32x3_supported(M, Nout, K, x, ldx, w, ldw),
               "abx_gemm_tf32x3: K, ldx, ldw must be multiples of 4 with ldx, ldw >= K, and x, w 16-byte aligned "
@@ -921,15 +923,30 @@ extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float
   }
   ABX_REQUIRE(transpose_n >= 0 && (transpose_n == 0 || M % (transpose_n * transpose_n) == 0),
               "abx_gemm_tf32x3: M must be a multiple of transpose_n^2");
+  ABX_REQUIRE(w_lo == nullptr || ((uintptr_t)w_lo & 15) == 0, "abx_gemm_tf32x3: w_lo must be 16-byte aligned");
   return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, residual, gate, row_scale, act,
-                                 transpose_n, y, ldy, tile_n);
+                                 transpose_n, y, ldy, tile_n, 0, 0, w_lo);
+}
+
+extern "C" int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
+                               const float* bias, const float* residual, const float* gate, const float* row_scale,
+                               int act, int transpose_n, float* y, int ldy, int tile_n) {
+  return abx_gemm_tf32x3_wlo(stream, M, Nout, K, x, ldx, w, nullptr, ldw, bias, residual, gate, row_scale, act, transpose_n, y, ldy,
+                             tile_n);
+}
+
+extern "C" int abx_gemm_tf32x3_glu_cm_wlo(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w,
+                                          const float* w_lo, int ldw, const float* bias, const float* row_scale, int n, int np,
+                                          float* y) {
+  ABX_REQUIRE(M > 0 && Nout > 0 && K > 0 && x && w && y, "abx_gemm_tf32x3_glu_cm: bad shape or null argument");
+  ABX_REQUIRE(abx::gemm_tf32x3_supported(M, Nout, K, x, ldx, w, ldw), "abx_gemm_tf32x3_glu_cm: unsupported operand layout");
+  ABX_REQUIRE(Nout % 128 == 0 && n > 0 && np >= n && M % (n * n) == 0, "abx_gemm_tf32x3_glu_cm: Nout %% 128, M %% n^2 and np >= n required");
+  ABX_REQUIRE(w_lo == nullptr || ((uintptr_t)w_lo & 15) == 0, "abx_gemm_tf32x3_glu_cm: w_lo must be 16-byte aligned");
+  return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, nullptr, nullptr, row_scale, 5, 0, y,
+                                 Nout / 2, 128, n, np, w_lo);
 }
 
 extern "C" int abx_gemm_tf32x3_glu_cm(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                                       const float* bias, const float* row_scale, int n, int np, float* y) {
-  ABX_REQUIRE(M > 0 && Nout > 0 && K > 0 && x && w && y, "abx_gemm_tf32x3_glu_cm: bad shape or null argument");
-  ABX_REQUIRE(abx::gemm_tf32x3_supported(M, Nout, K, x, ldx, w, ldw), "abx_gemm_tf32x3_glu_cm: unsupported operand layout");
-  ABX_REQUIRE(Nout % 128 == 0 && n > 0 && np >= n && M % (n * n) == 0, "abx_gemm_tf32x3_glu_cm: Nout %% 128, M %% n^2 and np >= n required");
-  return abx::launch_gemm_tf32x3((cudaStream_t)stream, M, Nout, K, x, ldx, w, ldw, bias, nullptr, nullptr, row_scale, 5, 0, y,
-                                 Nout / 2, 128, n, np);
+  return abx_gemm_tf32x3_glu_cm_wlo(stream, M, Nout, K, x, ldx, w, nullptr, ldw, bias, row_scale, n, np, y);
 }

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kGemmThreads) linear_f32_kernel(
 bool gemm_tf32x3_supported(int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw);
 int launch_gemm_tf32x3(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                        const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
-                       int transpose_n, float* y, int ldy, int tile_n, int cm_n, int cm_np);
+                       int transpose_n, float* y, int ldy, int tile_n, int cm_n, int cm_np, const float* w_lo);
 
 static int g_backend = 0;   // 0 auto (tensor cores when the operands qualify), 1 SIMT only, 2 tensor cores only
 int gemm_backend() { return g_backend; }
@@ -106,7 +106,7 @@ int gemm_backend() { return g_backend; }
 int launch_linear_f32(cudaStream_t s, int M, int Nout, int K, const float* x, int ldx, const float* w,
                       const float* bias, const float* residual, int relu, float* y, int ldy) {
   if (g_backend != 1 && M >= 32 && gemm_tf32x3_supported(M, Nout, K, x, ldx, w, K))
-    return launch_gemm_tf32x3(s, M, Nout, K, x, ldx, w, K, bias, residual, nullptr, nullptr, relu ? 1 : 0, 0, y, ldy, 0, 0, 0);
+    return launch_gemm_tf32x3(s, M, Nout, K, x, ldx, w, K, bias, residual, nullptr, nullptr, relu ? 1 : 0, 0, y, ldy, 0, 0, 0, nullptr);
   if (g_backend == 2) {
     set_error("linear: operands do not qualify for the tcgen05 path (M=%d Nout=%d K=%d ldx=%d)", M, Nout, K, ldx);
     return ABX_ERR_INVALID;

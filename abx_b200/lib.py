@@ -43,7 +43,9 @@ SIGNATURES = {
     'abx_igso3_build_tables': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'abx_linear_f32': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i]),
     'abx_gemm_tf32x3': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i]),
+    'abx_gemm_tf32x3_wlo': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i]),
     'abx_gemm_tf32x3_glu_cm': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    'abx_gemm_tf32x3_glu_cm_wlo': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     'abx_gemm_tf32x3_batched_nt': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
     'abx_layernorm_cm': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, C.c_float, _vp]),
     'abx_pair_input': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),

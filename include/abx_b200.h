@@ -131,6 +131,12 @@ int abx_linear_f32(void* stream, int M, int Nout, int K, const float* x, int ldx
 int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                     const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
                     int transpose_n, float* y, int ldy, int tile_n);
+/* Same with the low part of a STATIC weight supplied by the caller: w_lo[i] = w[i] - tf32_trunc(w[i]) (tf32_trunc clears the
+ * 13 low mantissa bits), same layout as w; NULL = split inside the kernel.  The kernel then fetches both parts by TMA and its
+ * converter warps only handle the activations (shorter load -> convert -> MMA latency per k-slab). */
+int abx_gemm_tf32x3_wlo(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, const float* w_lo, int ldw,
+                        const float* bias, const float* residual, const float* gate, const float* row_scale, int act,
+                        int transpose_n, float* y, int ldy, int tile_n);
 
 /* Triangle multiplication (seqformer.py:413-504) on the tensor cores, three calls:
  * (1) abx_gemm_tf32x3_glu_cm: the left/right projections and gates of LN(pair) as ONE GEMM with the GLU epilogue
@@ -142,6 +148,8 @@ int abx_gemm_tf32x3(void* stream, int M, int Nout, int K, const float* x, int ld
  * The incoming orientation uses the same calls on the transposed LN output (abx_layernorm transpose_n). */
 int abx_gemm_tf32x3_glu_cm(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, int ldw,
                            const float* bias, const float* row_scale, int n, int np, float* y);
+int abx_gemm_tf32x3_glu_cm_wlo(void* stream, int M, int Nout, int K, const float* x, int ldx, const float* w, const float* w_lo,
+                               int ldw, const float* bias, const float* row_scale, int n, int np, float* y);   /* w_lo: see above */
 int abx_gemm_tf32x3_batched_nt(void* stream, int batches, int n, int kpad, int inner, int outer_rows, int total_rows,
                                const float* a, const float* b, float* out, int ldo);
 int abx_layernorm_cm(void* stream, int B, int C, int n, int np, const float* x, const float* gamma, const float* beta,
