@@ -736,15 +736,14 @@ int sm_count() {
   return n;
 }
 
-// The tensor core ignores the 13 low mantissa bits of a tf32 operand (verified bit for bit on B200 by
-// tools/gemm_trunc_probe.py), so the raw fp32 tile already acts as the hi part and the converters only write
-// the lo tile.  ABX_GEMM_TRUST_TRUNC=0 restores the explicit hi write-back.
+// Run-time switches of the kernel (the `trust_trunc` argument, named after its first use).  The tensor core ignores the 13 low
+// mantissa bits of a tf32 operand read from shared memory (verified bit for bit on B200 in round 1 with an explicit-hi-write-back build of this kernel), so the raw
+// W tile already acts as its hi part and only the lo tile is written; the A operand in tensor memory is masked explicitly.
 int trust_trunc() {
   static int v = [] {
-    const char* e = getenv("ABX_GEMM_TRUST_TRUNC");
     const char* d = getenv("ABX_GEMM_DEBUG_SKIP");      // timing experiments only: 2 skip split, 4 skip MMA, 8 skip drain, 16 skip TMA
     const char* pf = getenv("ABX_GEMM_PROF");           // per-role cycle counters of CTA 0 (abx_gemm_profile)
-    return ((e && e[0] == '0') ? 0 : 1) | (d ? (atoi(d) & 30) : 0) | ((pf && pf[0] == '1') ? 32 : 0);
+    return 1 | (d ? (atoi(d) & 30) : 0) | ((pf && pf[0] == '1') ? 32 : 0);
   }();
   return v;
 }
