@@ -68,3 +68,30 @@ def test_gemm_glu_epilogue(cuda_device):
     ref = (lin[:, :, 0] * torch.sigmoid(lin[:, :, 1])).reshape(m, 256) * rs.double()[:, None]
     assert y.shape == (m, 256)
     assert maxabs(y.cpu(), ref.cpu()) < 3e-6 * float(ref.abs().max())
+
+
+def test_gemm_precomputed_weight_lo_matches_in_kernel_split(cuda_device):
+    """abx_gemm_tf32x3_wlo with the caller's w - tf32_trunc(w) must give the bits of the in-kernel split (w_lo = NULL), and the
+    per-weight cache of ops.weight_lo must follow in-place updates of the weight (load_state_dict bumps `_version`)."""
+    from abx_b200 import lib, ops
+    L = lib.load()
+    m, n, k = 1000, 192, 192
+    x, w, b = np_randn(11, m, k).cuda(), np_randn(12, n, k).cuda(), np_randn(13, n).cuda()
+
+    def run(w_lo):
+        y = torch.empty(m, n, device='cuda')
+        lib.check(L.abx_gemm_tf32x3_wlo(lib.stream(), m, n, k, lib.ptr(x), k, lib.ptr(w), lib.ptr(w_lo), k, lib.ptr(b), None, None, None,
+                                        0, 0, lib.ptr(y), n, 0))
+        return y
+
+    lo = ops.weight_lo(w)
+    assert lo is not None and torch.equal(lo, w - (w.view(torch.int32) & -8192).view(torch.float32))
+    assert float((lo.abs() / w.abs().clamp(min=1e-30)).max()) < 2 ** -10
+    assert torch.equal(run(lo), run(None))
+    y0 = ops.linear(x, w, b)
+    w.mul_(1.5)                                            # in place: same storage, new version
+    y1 = ops.linear(x, w, b)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    assert maxabs(y1.cpu(), ref.cpu()) < 3e-6 * float(ref.abs().max())
+    assert maxabs(y0.cpu(), ref.cpu()) > 1e-2            # the stale result is far away: the cache did notice the update
+    assert ops.weight_lo(torch.zeros(2048, 1024, device='cuda')) is None      # large weights: split inside the kernel
