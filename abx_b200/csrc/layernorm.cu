@@ -79,33 +79,44 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(
 // y [B, n, n, C]: the 'b c i j -> b i j c' rearrange + final LayerNorm after the triangle-multiplication product
 // (seqformer.py:500-502).  One CTA per (b, i, 32 values of j): coalesced 128-byte reads along j, transpose
 // through shared memory, warp reductions over the C <= 128 channels, coalesced writes along c.
-__global__ void __launch_bounds__(128) layernorm_cm_kernel(int C, int n, int np, const float* __restrict__ x,
+template <int C>
+__global__ void __launch_bounds__(128) layernorm_cm_kernel(int n, int np, const float* __restrict__ x,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            float eps, float* __restrict__ y) {
-  __shared__ float t[128][33];
+  __shared__ float t[C][33];
   const int j0 = blockIdx.x * 32, i = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = warp; c < C; c += 4) {
+  {
+    // compile-time trip count: all C / 4 loads of a thread are in flight before the first shared-memory store
     const int j = j0 + lane;
-    t[c][lane] = (j < n) ? x[(((size_t)b * C + c) * n + i) * np + j] : 0.f;
+    const float* xp = x + (((size_t)b * C + warp) * n + i) * np + j;
+    const size_t cstride = (size_t)4 * n * np;
+    float v[C / 4];
+#pragma unroll
+    for (int k = 0; k < C / 4; ++k) v[k] = (j < n) ? __ldg(xp + k * cstride) : 0.f;
+#pragma unroll
+    for (int k = 0; k < C / 4; ++k) t[warp + 4 * k][lane] = v[k];
   }
   __syncthreads();
-  const int nc = C / 32;                         // channels per lane
+  constexpr int nc = C / 32;                     // channels per lane
+  float g[nc], be[nc];
+#pragma unroll
+  for (int k = 0; k < nc; ++k) { g[k] = __ldg(gamma + lane + 32 * k); be[k] = __ldg(beta + lane + 32 * k); }
+#pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
     const int jl = warp * 8 + jj, j = j0 + jl;
     if (j >= n) break;
-    float v[4], sum = 0.f;
+    float v[nc], sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { v[k] = (k < nc) ? t[lane + 32 * k][jl] : 0.f; sum += v[k]; }
+    for (int k = 0; k < nc; ++k) { v[k] = t[lane + 32 * k][jl]; sum += v[k]; }
     const float mean = warp_sum(sum) / (float)C;
     float sq = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if (k < nc) { const float d = v[k] - mean; sq += d * d; }
+    for (int k = 0; k < nc; ++k) { const float d = v[k] - mean; sq += d * d; }
     const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
     float* yr = y + (((size_t)b * n + i) * n + j) * C;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (k < nc) { const int c = lane + 32 * k; yr[c] = (v[k] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c); }
+    for (int k = 0; k < nc; ++k) yr[lane + 32 * k] = (v[k] - mean) * rstd * g[k] + be[k];
   }
 }
 
@@ -117,7 +128,14 @@ extern "C" int abx_layernorm_cm(void* stream, int B, int C, int n, int np, const
   ABX_REQUIRE(B > 0 && n > 0 && np >= n && x && gamma && beta && y, "abx_layernorm_cm: bad shape or null argument");
   ABX_REQUIRE(C % 32 == 0 && C <= 128, "abx_layernorm_cm: C must be a multiple of 32 and <= 128 (got %d)", C);
   ABX_REQUIRE(n <= 65535 && B <= 65535, "abx_layernorm_cm: n and B must be <= 65535");
-  layernorm_cm_kernel<<<dim3((n + 31) / 32, n, B), 128, 0, (cudaStream_t)stream>>>(C, n, np, x, gamma, beta, eps, y);
+  const dim3 grid((n + 31) / 32, n, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 32: layernorm_cm_kernel<32><<<grid, 128, 0, st>>>(n, np, x, gamma, beta, eps, y); break;
+    case 64: layernorm_cm_kernel<64><<<grid, 128, 0, st>>>(n, np, x, gamma, beta, eps, y); break;
+    case 96: layernorm_cm_kernel<96><<<grid, 128, 0, st>>>(n, np, x, gamma, beta, eps, y); break;
+    default: layernorm_cm_kernel<128><<<grid, 128, 0, st>>>(n, np, x, gamma, beta, eps, y); break;
+  }
   count_launch();
   return check_launch("layernorm_cm_kernel");
 }

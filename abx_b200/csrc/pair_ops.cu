@@ -23,7 +23,9 @@ __global__ void __launch_bounds__(kPiWarps * 32) pair_input_kernel(
   const long long row = (long long)blockIdx.x * kPiWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nv = C >> 2;
-  const long long b = row / nn, ij = row % nn;
+  // 32-bit index arithmetic (the host checks rows < 2^31): a 64-bit division costs ~100 instructions, and this kernel is a
+  // pure stream (one row = 768 bytes in, 768 out)
+  const unsigned r32 = (unsigned)row, b = r32 / (unsigned)nn, ij = r32 - b * (unsigned)nn;
   float4 v[kPiMaxV];
   float sum = 0.f;
   const float4* pr = prev ? reinterpret_cast<const float4*>(prev + row * C) : nullptr;
@@ -51,8 +53,8 @@ __global__ void __launch_bounds__(kPiWarps * 32) pair_input_kernel(
     if (i4 >= nv) continue;
     const int c0 = 4 * i4;
     float4 o;                                         // concat(static, te, te): channel blocks never straddle a float4
-    if (c0 < Cs) o = __ldg(reinterpret_cast<const float4*>(stat + ij * Cs + c0));
-    else o = __ldg(reinterpret_cast<const float4*>(te + b * Ct + ((c0 - Cs) % Ct)));
+    if (c0 < Cs) o = __ldg(reinterpret_cast<const float4*>(stat + (size_t)ij * Cs + c0));
+    else { const int t0 = c0 - Cs; o = __ldg(reinterpret_cast<const float4*>(te + (size_t)b * Ct + (t0 >= Ct ? t0 - Ct : t0))); }
     if (pr) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i4), be = __ldg(reinterpret_cast<const float4*>(beta) + i4);
       // (static + LN(prev)) + emb, in the reference's order of additions
@@ -64,25 +66,22 @@ __global__ void __launch_bounds__(kPiWarps * 32) pair_input_kernel(
   }
 }
 
-__global__ void __launch_bounds__(256) outer_product_kernel(int B, int N, int C, const float* __restrict__ left,
+// grid (ceil(N q / 256), N, B) with q = 2C/4 float4 per output row: thread = one float4 of row (b, i, j) — all index arithmetic
+// in 32 bits (the flat 64-bit div / mod chain of the first version made this write-only stream issue-bound at 1.3 TB/s)
+__global__ void __launch_bounds__(256) outer_product_kernel(int N, int C, const float* __restrict__ left,
                                                             const float* __restrict__ right, float* __restrict__ out) {
-  // thread = one float4 of one output row (b,i,j); 2C/4 float4 per row
-  const int q = (2 * C) >> 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * N * N * q;
-  if (idx >= total) return;
-  const int f = (int)(idx % q);
-  const long long row = idx / q;
-  const int j = (int)(row % N);
-  const long long bi = row / N;
-  const int i = (int)(bi % N), b = (int)(bi / N);
-  const int c0 = (4 * f) % C;
+  const unsigned q = (unsigned)(2 * C) >> 2;
+  const unsigned t = blockIdx.x * 256u + threadIdx.x;          // (j, f) flattened
+  if (t >= (unsigned)N * q) return;
+  const unsigned j = t / q, f = t - j * q;
+  const unsigned i = blockIdx.y, b = blockIdx.z;
+  const unsigned c0 = 4 * f >= (unsigned)C ? 4 * f - C : 4 * f;
   const float4 l = __ldg(reinterpret_cast<const float4*>(left + ((size_t)b * N + j) * C + c0));
   const float4 r = __ldg(reinterpret_cast<const float4*>(right + ((size_t)b * N + i) * C + c0));
   float4 o;
-  if (4 * f < C) o = make_float4(l.x * r.x, l.y * r.y, l.z * r.z, l.w * r.w);
+  if (4 * f < (unsigned)C) o = make_float4(l.x * r.x, l.y * r.y, l.z * r.z, l.w * r.w);
   else o = make_float4(l.x - r.x, l.y - r.y, l.z - r.z, l.w - r.w);
-  reinterpret_cast<float4*>(out)[idx] = o;
+  reinterpret_cast<float4*>(out)[((size_t)b * N + i) * N * q + t] = o;
 }
 
 }  // namespace abx
@@ -98,7 +97,7 @@ extern "C" int abx_pair_input(void* stream, int B, int N, int C, int Cs, int Ct,
   ABX_REQUIRE(!prev_pos || emb, "abx_pair_input: prev_pos needs the embedding table");
   const long long rows = (long long)B * N * N;
   const long long blocks = (rows + kPiWarps - 1) / kPiWarps;
-  ABX_REQUIRE(blocks < 2147483647LL, "abx_pair_input: too many rows");
+  ABX_REQUIRE(rows < 2147483647LL, "abx_pair_input: too many rows");
   pair_input_kernel<<<(unsigned)blocks, kPiWarps * 32, 0, (cudaStream_t)stream>>>(
       rows, N * N, C, Cs, Ct, stat, te, prev_pair, gamma, beta, eps, reinterpret_cast<const long long*>(prev_pos), emb, y);
   count_launch();
@@ -108,10 +107,8 @@ extern "C" int abx_pair_input(void* stream, int B, int N, int C, int Cs, int Ct,
 extern "C" int abx_outer_product(void* stream, int B, int N, int C, const float* left, const float* right, float* out) {
   using namespace abx;
   ABX_REQUIRE(B > 0 && N > 0 && C > 0 && C % 4 == 0 && left && right && out, "abx_outer_product: bad shape or null argument");
-  const long long total = (long long)B * N * N * (2 * C / 4);
-  const long long blocks = (total + 255) / 256;
-  ABX_REQUIRE(blocks < 2147483647LL, "abx_outer_product: too many elements");
-  outer_product_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, N, C, left, right, out);
+  ABX_REQUIRE(N <= 65535 && B <= 65535 && (long long)N * (2 * C / 4) < 2147483647LL, "abx_outer_product: N, B must be <= 65535");
+  outer_product_kernel<<<dim3((unsigned)((N * (2 * C / 4) + 255) / 256), N, B), 256, 0, (cudaStream_t)stream>>>(N, C, left, right, out);
   count_launch();
   return check_launch("outer_product_kernel");
 }
