@@ -894,56 +894,80 @@ ipa_fused_kernel(int N, int R, int tiles_per_b, int zslots, const float* __restr
 
 // ---------------------------------------------------------------------------------------------------
 // chunked key-major pair bias: out[b][c][i][12 k + h] = sqrt(1/3) (z[b,i,8c+k,:] . w[h,:] + b[h])   folding.py:101-104
-// One CTA per (b, i, 64-key tile): the z tile is staged in shared memory (row stride 132 floats: conflict-free
-// float4 reads with lanes on consecutive keys), thread = (key, group of 6 heads).
+// Persistent CTAs walk the (b, i, 128-key tile) list; the z tile is staged in shared memory by cp.async (row stride 132
+// floats: conflict-free float4 reads with lanes on consecutive keys), the weights once per CTA; three CTAs per SM overlap
+// each other's copy and compute phases.  thread = (2 keys, 6 heads): a 16-byte shared-memory read costs four passes whether it
+// is a broadcast or not, so the weight reads (6 per 4 channels) dominate — with two keys per thread they are shared by twice
+// the multiply-adds (the first version, one key per thread, sat at 3.1 TB/s on exactly that).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kBiasJ = 64, kZld = kCz + 4, kBiasThreads = 128;
+constexpr int kBiasJ = 128, kZld = kCz + 4, kBiasThreads = 128;
+constexpr size_t kBiasSmem = (size_t)(kBiasJ * kZld + kH * kCz) * sizeof(float);
 
-__global__ void __launch_bounds__(kBiasThreads) ipa_pair_bias_chunked_kernel(int N, const float* __restrict__ z,
+__global__ void __launch_bounds__(kBiasThreads) ipa_pair_bias_chunked_kernel(int N, int tiles_per_row, int total_tiles,
+                                                                             const float* __restrict__ z,
                                                                              const float* __restrict__ w_pair,
                                                                              const float* __restrict__ b_pair,
                                                                              float* __restrict__ bias) {
-  __shared__ __align__(16) float zs[kBiasJ * kZld];
-  __shared__ __align__(16) float ws[kH * kCz];
-  const int j0 = blockIdx.x * kBiasJ, i = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) float bias_smem[];
+  float* zs = bias_smem;                              // [kBiasJ * kZld]
+  float* ws = bias_smem + kBiasJ * kZld;              // [kH * kCz]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunks = (N + kChunk - 1) / kChunk;
   for (int k = tid; k < kH * kCz / 4; k += kBiasThreads)
     reinterpret_cast<float4*>(ws)[k] = __ldg(reinterpret_cast<const float4*>(w_pair) + k);
-  const float4* zrow = reinterpret_cast<const float4*>(z + (((size_t)b * N + i) * N + j0) * kCz);
-  const int nj = min(kBiasJ, N - j0);
-#pragma unroll 4
-  for (int k = tid; k < nj * (kCz / 4); k += kBiasThreads) {
-    const int jj = k / (kCz / 4), c4 = k % (kCz / 4);
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(zrow + k));
-    *reinterpret_cast<float4*>(&zs[jj * kZld + 4 * c4]) = v;
-  }
-  __syncthreads();
-  // thread = (key, 6 heads): one 16-byte z read feeds 24 multiply-adds (12 FFMA2); the weight reads are warp-wide broadcasts
-  const int jj = tid % kBiasJ, hg = tid / kBiasJ;     // heads 6 hg .. 6 hg + 5
-  if (jj >= nj) return;
-  float2 acc[6];
-#pragma unroll
-  for (int u = 0; u < 6; ++u) acc[u] = make_float2(0.f, 0.f);
-#pragma unroll 4
-  for (int c = 0; c < kCz; c += 4) {
-    const float4 zv = *reinterpret_cast<const float4*>(&zs[jj * kZld + c]);
-    const float2 za = make_float2(zv.x, zv.y), zb = make_float2(zv.z, zv.w);
-#pragma unroll
-    for (int u = 0; u < 6; ++u) {
-      const float4 wv = *reinterpret_cast<const float4*>(&ws[(6 * hg + u) * kCz + c]);
-      acc[u] = ffma2(za, make_float2(wv.x, wv.y), acc[u]);
-      acc[u] = ffma2(zb, make_float2(wv.z, wv.w), acc[u]);
-    }
-  }
+  const int hg = warp >> 1;                           // heads 6 hg .. 6 hg + 5
+  const int ka = (warp & 1) * 64 + lane, kb = ka + 32; // this thread's two keys of the tile
+  float bsc[6];
   const float w_pair_scale = sqrtf(1.0f / 3.0f);
-  const int j = j0 + jj;
-  float* dst = bias + (((size_t)b * nchunks + j / kChunk) * N + i) * kBiasRow + (j % kChunk) * kH + 6 * hg;
 #pragma unroll
-  for (int u = 0; u < 6; u += 2)
-    *reinterpret_cast<float2*>(dst + u) = make_float2(w_pair_scale * ((acc[u].x + acc[u].y) + __ldg(b_pair + 6 * hg + u)),
-                                                      w_pair_scale * ((acc[u + 1].x + acc[u + 1].y) + __ldg(b_pair + 6 * hg + u + 1)));
+  for (int u = 0; u < 6; ++u) bsc[u] = __ldg(b_pair + 6 * hg + u);
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    // tile t -> (row = b N + i, 128-key tile jt); all in 32 bits
+    const unsigned row = (unsigned)t / (unsigned)tiles_per_row, jt = (unsigned)t - row * (unsigned)tiles_per_row;
+    const unsigned b = row / (unsigned)N, i = row - b * (unsigned)N;
+    const int j0 = (int)jt * kBiasJ, nj = min(kBiasJ, N - j0);
+    const float4* zrow = reinterpret_cast<const float4*>(z + ((size_t)row * N + j0) * kCz);
+    for (int k = tid; k < nj * (kCz / 4); k += kBiasThreads) {
+      const int jj = k / (kCz / 4), c4 = k % (kCz / 4);
+      const uint32_t sa = (uint32_t)__cvta_generic_to_shared(zs + jj * kZld + 4 * c4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(zrow + k) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // the tile (and, the first time, the weights) are in shared memory
+    if (ka < nj) {
+      const bool two = kb < nj;
+      const float* za_p = zs + ka * kZld;
+      const float* zb_p = zs + (two ? kb : ka) * kZld;
+      float2 acc[2][6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) acc[0][u] = acc[1][u] = make_float2(0.f, 0.f);
+#pragma unroll 4
+      for (int c = 0; c < kCz; c += 4) {
+        const float4 za = *reinterpret_cast<const float4*>(za_p + c), zb = *reinterpret_cast<const float4*>(zb_p + c);
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const float4 wv = *reinterpret_cast<const float4*>(&ws[(6 * hg + u) * kCz + c]);
+          const float2 w0 = make_float2(wv.x, wv.y), w1 = make_float2(wv.z, wv.w);
+          acc[0][u] = ffma2(make_float2(za.x, za.y), w0, acc[0][u]);
+          acc[0][u] = ffma2(make_float2(za.z, za.w), w1, acc[0][u]);
+          acc[1][u] = ffma2(make_float2(zb.x, zb.y), w0, acc[1][u]);
+          acc[1][u] = ffma2(make_float2(zb.z, zb.w), w1, acc[1][u]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q == 1 && !two) break;
+        const int j = j0 + (q ? kb : ka);
+        float* dst = bias + (((size_t)b * nchunks + j / kChunk) * N + i) * kBiasRow + (j % kChunk) * kH + 6 * hg;
+#pragma unroll
+        for (int u = 0; u < 6; u += 2)
+          *reinterpret_cast<float2*>(dst + u) = make_float2(w_pair_scale * ((acc[q][u].x + acc[q][u].y) + bsc[u]),
+                                                            w_pair_scale * ((acc[q][u + 1].x + acc[q][u + 1].y) + bsc[u + 1]));
+      }
+    }
+    __syncthreads();                                   // the tile is overwritten by the next iteration's copy
+  }
 }
 
 // Tile height: time ~ rounds * (R + 6.4) — R rows of z per tile plus the tile's key / value chunks (3264 B per key
@@ -1001,7 +1025,13 @@ size_t ipa_fused_kvp_floats(int B, int N) { return (size_t)B * N * kKVRow; }
 size_t ipa_pair_bias_floats(int B, int N) { return (size_t)B * ceil_div(N, kChunk) * N * kBiasRow; }
 
 int launch_ipa_pair_bias(cudaStream_t s, int B, int N, const float* z, const float* w_pair, const float* b_pair, float* bias) {
-  ipa_pair_bias_chunked_kernel<<<dim3(ceil_div(N, kBiasJ), N, B), kBiasThreads, 0, s>>>(N, z, w_pair, b_pair, bias);
+  const int tiles_per_row = ceil_div(N, kBiasJ);
+  const long long total = (long long)B * N * tiles_per_row;
+  ABX_REQUIRE(total < 2147483647LL, "abx_ipa_pair_bias: too many tiles");
+  ABX_CUDA(cudaFuncSetAttribute(ipa_pair_bias_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBiasSmem));
+  const long long ctas = 3LL * fused_sm_count();      // 73.7 KB of shared memory each: three resident CTAs per SM
+  ipa_pair_bias_chunked_kernel<<<(unsigned)(total < ctas ? total : ctas), kBiasThreads, kBiasSmem, s>>>(N, tiles_per_row, (int)total, z,
+                                                                                                       w_pair, b_pair, bias);
   count_launch();
   return check_launch("ipa_pair_bias_chunked_kernel");
 }
