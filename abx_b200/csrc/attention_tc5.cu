@@ -201,6 +201,30 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Loader state lives at function scope so that the loader warps can issue the first K / V tile's loads BEFORE the Q staging
+  // (two HBM round trips of the prologue overlap instead of following each other).
+  const int t = threadIdx.x - 2 * kSoftThreads;      // 0..127 in the loader warps
+  constexpr int kPer = kTK * D4 / kLoadThreads;      // float4 per thread and matrix (D = 48: 6)
+  static_assert(kTK * D4 % kLoadThreads == 0, "tile must divide over the loader threads");
+  float4 kreg[kPer], vreg[kPer];
+  // K and V: thread <-> key (fastest) x a run of kPer consecutive 16-byte blocks of that key's row (whole 32-byte sectors per
+  // thread).  K stores: a warp writes one block of 32 consecutive keys = 512 contiguous bytes; V stores (transposing, scalar):
+  // 32 consecutive keys of one channel row = 32 distinct banks.
+  const int vkey = t & (kTK - 1), vc0 = (t / kTK) * kPer;
+  static_assert(kLoadThreads / kTK * kPer == D4, "mapping must cover the row");
+  auto fetch = [&](int kt) {                         // global -> registers (the next tile's loads are in flight during the math)
+    const int jv = kt * kTK + vkey;
+    const size_t ro = (row0 + (jv < L ? jv : 0)) * (size_t)ld + h * D + 4 * vc0;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      kreg[u] = vreg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (jv < L) {
+        kreg[u] = *reinterpret_cast<const float4*>(k + ro + 4 * u);
+        vreg[u] = *reinterpret_cast<const float4*>(v + ro + 4 * u);
+      }
+    }
+  };
+  if (warp >= 8 && warp < 12) fetch(0);
   // Q tiles of the slots, pre-multiplied by log2(e) / sqrt(D): hi / lo, K-major core matrices.  Thread <-> (row, half of the
   // row's 16-byte blocks) with the row fastest: a warp's stores of one block are 32 consecutive rows = 512 contiguous bytes.
   {
@@ -372,27 +396,6 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
   } else if (warp < 12) {
     // ================= loader warps: K / V tile -> hi / lo operand tiles, two stages =================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
-    const int t = threadIdx.x - 2 * kSoftThreads;    // 0..127
-    constexpr int kPer = kTK * D4 / kLoadThreads;    // float4 per thread and matrix (D = 48: 6)
-    static_assert(kTK * D4 % kLoadThreads == 0, "tile must divide over the loader threads");
-    float4 kreg[kPer], vreg[kPer];
-    // K and V: thread <-> key (fastest) x a run of kPer consecutive 16-byte blocks of that key's row (whole 32-byte sectors per
-    // thread).  K stores: a warp writes one block of 32 consecutive keys = 512 contiguous bytes; V stores (transposing, scalar):
-    // 32 consecutive keys of one channel row = 32 distinct banks.
-    const int vkey = t % kTK, vc0 = (t / kTK) * kPer;
-    static_assert(kLoadThreads / kTK * kPer == D4, "mapping must cover the row");
-    auto fetch = [&](int kt) {                       // global -> registers (the next tile's loads are in flight during the math)
-      const int jv = kt * kTK + vkey;
-      const size_t ro = (row0 + (jv < L ? jv : 0)) * (size_t)ld + h * D + 4 * vc0;
-#pragma unroll
-      for (int u = 0; u < kPer; ++u) {
-        kreg[u] = vreg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (jv < L) {
-          kreg[u] = *reinterpret_cast<const float4*>(k + ro + 4 * u);
-          vreg[u] = *reinterpret_cast<const float4*>(v + ro + 4 * u);
-        }
-      }
-    };
     auto split4 = [](const float4& x, float4& hi, float4& lo) {
       hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
       hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
@@ -415,8 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_attention_tc5_kernel(
         *reinterpret_cast<float*>(v_lo + vo + 32) = lo.z; *reinterpret_cast<float*>(v_lo + vo + 48) = lo.w;
       }
     };
-    fetch(0);
-    for (int kt = 0; kt < nkt; ++kt) {
+    for (int kt = 0; kt < nkt; ++kt) {                 // tile 0 was fetched in the prologue
       const int st = kt & 1;
       if (kt >= kStagesKV) ABX_ATTN_PWAIT(0, kv_empty + st, ((kt >> 1) - 1) & 1);   // the products of tile kt - 2 have read the stage
       stage(sm + SM::kv_base + st * SM::kStageBytes);
