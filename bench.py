@@ -120,8 +120,15 @@ class ClockSampler:
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(sm)}
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace('.', '').isdigit()]
+        out = {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+               'samples': len(sm)}
+        if sm:                                   # spread of the clock under the power cap: the step time follows it from box to box
+            q = sorted(sm)
+            out.update({'sm_mhz_mean': round(statistics.fmean(sm), 1), 'sm_mhz_p10': q[len(q) // 10], 'sm_mhz_min': q[0]})
+        if pw:
+            out.update({'power_w_mean': round(statistics.fmean(pw), 1), 'power_w_max': max(pw)})
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------
