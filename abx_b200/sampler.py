@@ -47,6 +47,7 @@ def _frame_output(batch, model_out, seq_t, diffuse_mask, antibody_len, t, to_hos
 
 
 STATE_KEYS = ('rigids_t', 'seq_t', 'prev_pos', 'prev_seq', 'prev_pair')
+T_KEYS = ('t', 'rot_score_scaling', 'trans_score_scaling')      # rewritten by _set_t_feats inside every iteration
 
 
 class GraphedReverseStep:
@@ -55,9 +56,15 @@ class GraphedReverseStep:
     launch, so the host never gates the GPU.  The iteration reads and writes five state tensors
     (STATE_KEYS) plus the scalar t; they live in static buffers that the graph's outputs are copied back into."""
 
+    replayed_launches = 0     # abx kernel launches executed through graph replays (bench.py's `gpu_launches`)
+
     def __init__(self, batch, step_fn, generator=None):
         dev = batch['rigids_t'].device
         self.batch = batch
+        self.generator = generator
+        self.step_fn = step_fn            # keeps the closure's tensors (masks, dt, placeholders) alive: the graph reads them by address
+        # everything else the captured iteration reads: a later batch may reuse this graph only if these are unchanged
+        self.features = {k: v for k, v in batch.items() if torch.is_tensor(v) and k not in STATE_KEYS and k not in T_KEYS}
         batch['rigids_t'] = batch['rigids_t'].to(torch.float64).contiguous()     # exact widening; reverse() returns float64
         batch['seq_t'] = batch['seq_t'].long().contiguous()
         self.state = {k: batch[k] for k in STATE_KEYS}
@@ -89,9 +96,36 @@ class GraphedReverseStep:
             self.state[k].copy_(v)
             self.batch[k] = self.state[k]
 
+    def matches(self, batch):
+        """True when `batch` holds the same step-invariant features (same keys, shapes, dtypes and values) as the batch this
+        graph was captured on — samples of the same complex: the graph (which reads the captured tensors) can serve it."""
+        feats = {k: v for k, v in batch.items() if torch.is_tensor(v) and k not in STATE_KEYS and k not in T_KEYS}
+        if feats.keys() != self.features.keys():
+            return False
+        for k, v in feats.items():
+            c = self.features[k]
+            if v.shape != c.shape or v.dtype != c.dtype or v.device != c.device:
+                return False
+        return all(v is self.features[k] or bool(torch.equal(v, self.features[k])) for k, v in feats.items())
+
+    def rebind(self, batch, generator=None):
+        """Serve a new batch of the same complex with the captured graph: its state is copied into the static buffers, which
+        the batch then refers to; the per-iteration entries the graph writes (`t`) are the captured batch's tensors (the loop's
+        last, eager forward reads the t of the last replayed iteration, as in the reference); the captured generator continues
+        the new generator's stream."""
+        for k in STATE_KEYS:
+            self.state[k].copy_(batch[k])
+            batch[k] = self.state[k]
+        for k in T_KEYS:
+            if k in self.batch:
+                batch[k] = self.batch[k]
+        if generator is not None and self.generator is not None and generator is not self.generator:
+            self.generator.set_state(generator.get_state())
+
     def __call__(self, t):
         self.t.fill_(float(t))
         self.graph.replay()
+        GraphedReverseStep.replayed_launches += getattr(GraphedReverseStep, 'last_captured_launches', 0)
         new_state, model_out = self.out
         for k in STATE_KEYS:
             self.state[k].copy_(new_state[k])
@@ -152,7 +186,20 @@ def sample_loop(data_init, config, diffuser, model, mode='design', num_t=100, mi
             if cuda_graph and len(reverse_steps) > 2:
                 if noise_fn is not None or trajectory or not (embed_sc and self_condition):
                     raise ValueError('cuda_graph=True needs the default self-conditioned design/optimize loop without noise_fn')
-                graphed = GraphedReverseStep(batch, reverse_iteration, generator=generator)
+                # One graph per (model, diffuser, loop settings, complex): chunks of samples of the same complex (bench.py's steps,
+                # the CLI's sample chunks) replay the graph captured for the first one instead of re-capturing ~3300 launches
+                # (eager warm-up + capture + instantiation: 0.3 s on a fast host, several times that on a busy one).
+                key = (id(diffuser), id(config_model), mode, float(dt), bool(center), float(noise_scale), generator is None,
+                       sum(p._version for p in model.parameters()))
+                cached = getattr(model, '_abx_graph_cache', None)
+                if cached is not None and cached[0] == key and cached[1].matches(batch):
+                    graphed = cached[1]
+                    graphed.rebind(batch, generator)
+                else:
+                    model._abx_graph_cache = None           # free the old graph's memory pool before capturing a new one
+                    graphed = GraphedReverseStep(batch, reverse_iteration, generator=generator)
+                    # the captured graph reads the static-embedding tensors of this call: they must outlive `clear_static()`
+                    model._abx_graph_cache = (key, graphed, trunk._static)
             for k, t in enumerate(reverse_steps):
                 if t > min_t:
                     if graphed is not None:

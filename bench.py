@@ -376,13 +376,14 @@ def run_b200(a):
     if rank == 0:
         clocks.start()
     lib.reset_launch_count()
+    sampler.GraphedReverseStep.replayed_launches = 0
     if not use_graph[0]:
         instrument(True)
     ms_total, _ = timed(a.steps, False, a.warmup)
     instrument(False)
     launches = torch.tensor([lib.launch_count()], device=dev, dtype=torch.int64)
-    if use_graph[0]:        # launches recorded while capturing replay once per reverse iteration
-        launches = launches + (n_forwards(a) - 3) * getattr(sampler.GraphedReverseStep, 'last_captured_launches', 0) * a.steps
+    if use_graph[0]:        # launches replayed from the captured graph (one capture serves all steps of the same complex)
+        launches = launches + sampler.GraphedReverseStep.replayed_launches
     if world > 1:
         dist.all_reduce(launches)
     clock_info = clocks.stop() if rank == 0 else None

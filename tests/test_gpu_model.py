@@ -173,6 +173,44 @@ def test_cuda_graph_replay_matches_eager_loop(cuda_device):
     assert maxabs(outs[0][0], outs[1][0]) < 1e-4 and maxabs(outs[0][2], outs[1][2]) < 1e-4
 
 
+def test_cuda_graph_is_reused_for_the_same_complex_and_recaptured_otherwise(cuda_device):
+    """A second chunk of samples of the same complex replays the graph captured for the first one (no re-capture) and gives
+    the bits a fresh capture gives; changed features or weights force a new capture."""
+    from abx_b200 import sampler as S
+    from tests.gpu_util import built_diffuser
+    g = golden('sampler')
+    cfg = model_config()
+    fd = built_diffuser()
+    model = make_model(fd)
+    batch = to_cuda(batch_from_golden(g))
+
+    def run(seed, b=batch):
+        gen = torch.Generator(device='cuda').manual_seed(seed)
+        traj, final = S.sample_loop(b, cfg, fd, model, num_t=6, generator=gen, cuda_graph=True)
+        return traj[-1]['atom14_results'].clone(), traj[-1]['seq'].clone(), final['rigids_t'].clone()
+
+    run(5)
+    first = model._abx_graph_cache[1]
+    cached = run(6)
+    assert model._abx_graph_cache[1] is first                      # reused
+    model._abx_graph_cache = None
+    fresh = run(6)
+    assert model._abx_graph_cache[1] is not first
+    for a, b_ in zip(cached, fresh):
+        assert torch.equal(a, b_)
+    second = model._abx_graph_cache[1]
+    moved = dict(batch)
+    moved['fixed_mask'] = batch['fixed_mask'].clone()
+    moved['fixed_mask'][..., :1] = 1 - moved['fixed_mask'][..., :1]      # another design region: features differ
+    run(6, moved)
+    assert model._abx_graph_cache[1] is not second                # re-captured
+    third = model._abx_graph_cache[1]
+    with torch.no_grad():
+        next(model.parameters()).mul_(1.0)                        # in-place weight update bumps the version
+    run(6, moved)
+    assert model._abx_graph_cache[1] is not third
+
+
 def test_inference_cli_end_to_end(cuda_device, tmp_path):
     """`inference.py` surface on a tiny .npz complex with seeded weights: output layout of inference.py:304-373."""
     import json
